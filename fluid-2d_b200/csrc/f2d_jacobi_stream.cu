@@ -1,0 +1,339 @@
+// f2d_jacobi_stream.cu -- temporally blocked Jacobi relaxation for sm_100a.
+//
+// Replaces the reference's relaxation loops (diffuse: src/fluid_solver_gpu.cu:301-311 with
+// diffuse_iteration_kernel :69-85; pressure: :379-391 with p_iteration_kernel :179-191), which
+// per sweep do a full-field D2D copy, one 2-D kernel, one 1-D boundary kernel and two device
+// syncs, i.e. >= 20 B of HBM traffic per cell per sweep.
+//
+// Design ("row streaming with a register pipeline"):
+//   * The field is cut into column strips of 128 floats (one float4 per lane of a warp) and row
+//     chunks.  ONE WARP owns one (strip, chunk) and marches down its rows.  No block-level
+//     synchronisation exists anywhere: warps are fully independent.
+//   * T sweeps are fused per pass.  For every time level s < T a lane keeps a sliding window of
+//     three rows (its four columns) in REGISTERS; when input row r arrives, level 1 can produce
+//     row r-1, level 2 row r-2, ... level T row r-T, which is stored.  North/south neighbours are
+//     therefore register reads, west/east neighbours are two warp shuffles per row, and each
+//     input row is read from HBM once and each output row written once per T sweeps
+//     (12/T bytes per cell-sweep instead of 12).
+//   * Redundant work exists only in the HALO columns left/right of a strip (HALO >= T) and the
+//     T warm-up rows above/below a chunk; validity shrinks by one cell per level from every
+//     non-domain edge, exactly covered by the halos.
+//   * Input rows are staged through a per-warp shared-memory ring with 16-byte asynchronous
+//     copies (cp.async.cg -> LDGSTS, L1-bypassing), PFD rows ahead, so HBM latency is hidden
+//     without spending registers; each lane only ever reads back the bytes it copied itself,
+//     so cp.async.wait_group is the only synchronisation needed.
+//   * The boundary pass (set_boundary_*, gpu.cu:11-54) is fused: domain edge columns are fixed
+//     inside the lane that holds them (columns 0/1 and N-2/N-1 share a float4 because cols%4==0),
+//     edge rows are produced by the edge rule when the adjacent interior row of the same level
+//     is produced; corners are carried through unchanged from the input (the reference never
+//     writes them, gpu.cu:15-23).
+//   * Arithmetic is spelled with intrinsics (f2d_common.cuh) so every level is bit-identical to
+//     one sweep of the naive kernel: T fused sweeps == T single sweeps, bitwise.
+//   * The row loop is unrolled by RS (a multiple of 3) so that all window/ring register indices
+//     are compile-time constants; blocks of RS rows in which every level is strictly inside the
+//     chunk take a FAST path without any range or edge-row checks.
+#include "f2d_kernels.cuh"
+
+namespace f2d {
+
+namespace {
+
+constexpr int kLanes = 32;
+constexpr int kStripFloats = 128;  // one float4 per lane
+constexpr int kPFD = 4;            // async prefetch distance in rows
+constexpr int kRingP = 8;          // ring slots for the iterate rows (power of two, >= PFD + 2)
+
+__host__ __device__ constexpr int halo_of(int T) { return T <= 4 ? 4 : ((T + 3) / 4) * 4; }
+__host__ __device__ constexpr int m3(int x) { return ((x % 3) + 3) % 3; }
+__host__ __device__ constexpr int rs_of(int T) { return 3 * ((T + 1 + 2) / 3); }  // rhs register ring
+__host__ __device__ constexpr int mrs(int x, int RS) { return ((x % RS) + RS) % RS; }
+// rhs smem ring slots (power of two): register mode only needs the landing zone,
+// smem mode keeps rows r+PFD .. r-T
+__host__ __device__ constexpr int ring_r_of(int T, bool rhs_regs) {
+    return rhs_regs ? kRingP : ((kPFD + T + 2) <= 8 ? 8 : 16);
+}
+
+struct StreamPlan {
+    int strips, chunks, chunk_rows, bw;
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <bool DIFFUSE, int DIVMODE>
+__device__ __forceinline__ float4 relax_row(const float4& a, const float4& b, const float4& c, float l, float rt,
+                                            const float4& rhs, const DiffuseCoef& k) {
+    float4 o;
+    if (DIFFUSE) {
+        o.x = diffuse_update<DIVMODE>(l, b.y, a.x, c.x, rhs.x, k);
+        o.y = diffuse_update<DIVMODE>(b.x, b.z, a.y, c.y, rhs.y, k);
+        o.z = diffuse_update<DIVMODE>(b.y, b.w, a.z, c.z, rhs.z, k);
+        o.w = diffuse_update<DIVMODE>(b.z, rt, a.w, c.w, rhs.w, k);
+    } else {
+        o.x = pressure_update(rhs.x, b.y, l, c.x, a.x);
+        o.y = pressure_update(rhs.y, b.z, b.x, c.y, a.y);
+        o.z = pressure_update(rhs.z, b.w, b.y, c.z, a.z);
+        o.w = pressure_update(rhs.w, rt, b.z, c.w, a.w);
+    }
+    return o;
+}
+
+// edge row from the adjacent interior row of the same level; corner cells keep `keep`
+__device__ __forceinline__ float4 edge_row(const float4& inner, const float4& keep, bool neg, bool has_left,
+                                           bool has_right) {
+    float4 o;
+    o.x = apply_sign(inner.x, neg);
+    o.y = apply_sign(inner.y, neg);
+    o.z = apply_sign(inner.z, neg);
+    o.w = apply_sign(inner.w, neg);
+    if (has_left) o.x = keep.x;
+    if (has_right) o.w = keep.w;
+    return o;
+}
+
+// per-warp constants of one (strip, chunk)
+struct Ctx {
+    const float* prev;  // lane-adjusted: + column of this lane
+    const float* rhs;
+    float* next;
+    float4* ring_p;  // lane-adjusted: + lane
+    float4* ring_r;
+    DiffuseCoef coef;
+    int pitch, rs, re, y0, y1;
+    int cp_bytes;
+    bool top_dom, bot_dom, own_x, has_left, has_right, edge_warp, neg_c, neg_r;
+};
+
+// RS consecutive row steps starting at relative row rb (a multiple of RS, so rb % 3 == 0 and the
+// register slots of every row are compile-time constants).
+template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS, bool FAST, int RS, int RINGR, int NRH>
+__device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, float4 (&W)[T][3], float4 (&RH)[NRH],
+                                          float4& out_prev) {
+#pragma unroll
+    for (int k = 0; k < RS; ++k) {
+        const int rr = rb + k;
+        if (!FAST && rr >= nsteps) break;
+        const int r = cx.rs + rr;
+
+        // 1. keep PFD rows in flight
+        {
+            const int rl = r + kPFD;
+            if (rl <= cx.re) {
+                const size_t off = (size_t)rl * cx.pitch;
+                if (!PIN_ZERO) cp_async16(cx.ring_p + (rl & (kRingP - 1)) * kLanes, cx.prev + off, cx.cp_bytes);
+                cp_async16(cx.ring_r + (rl & (RINGR - 1)) * kLanes, cx.rhs + off, cx.cp_bytes);
+            }
+            cp_async_commit();
+        }
+        // 2. row r has landed (each lane reads back only the 16 bytes it copied itself)
+        cp_async_wait<kPFD>();
+        if (FAST || r <= cx.re) {
+            if (!PIN_ZERO)
+                W[0][m3(k)] = cx.ring_p[(r & (kRingP - 1)) * kLanes];
+            else
+                W[0][m3(k)] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RHS_REGS) RH[mrs(k, RS)] = cx.ring_r[(r & (RINGR - 1)) * kLanes];
+        }
+
+        // 3. level s+1 produces row q = r - s - 1 from level s rows q-1, q, q+1.
+        //    active levels: rs+1 <= q <= re-1  <=>  s_lo <= s <= s_hi
+        const int s_lo = r - cx.re, s_hi = r - cx.rs - 2;
+        const int s_top = cx.top_dom ? r - 2 : -1;           // level whose q == 1 (global top edge above it)
+        const int s_bot = cx.bot_dom ? r - cx.re - 1 : -1;   // level whose q == re == global bottom edge row
+#pragma unroll
+        for (int s = 0; s < T; ++s) {
+            const int q = r - s - 1;
+            const int sa = m3(k - s - 2), sm = m3(k - s - 1), sc = m3(k - s);
+            const int sn = (s + 1 < T) ? s + 1 : 0;  // keeps the dead branch's index in range
+            if (FAST || (s >= s_lo && s <= s_hi)) {
+                const float4 a = W[s][sa], b = W[s][sm], c = W[s][sc];
+                const float l = __shfl_up_sync(0xffffffffu, b.w, 1);
+                const float rt = __shfl_down_sync(0xffffffffu, b.x, 1);
+                float4 rhs;
+                if (RHS_REGS)
+                    rhs = RH[mrs(k - s - 1, RS)];
+                else
+                    rhs = cx.ring_r[(q & (RINGR - 1)) * kLanes];
+                float4 nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
+                if (cx.edge_warp) {  // warp-uniform: this strip touches the left/right domain edge
+                    // interior rows: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32)
+                    if (cx.has_left) nw.x = apply_sign(nw.y, cx.neg_c);
+                    if (cx.has_right) nw.w = apply_sign(nw.z, cx.neg_c);
+                }
+                if (s + 1 < T) {
+                    W[sn][sm] = nw;
+                } else {
+                    out_prev = nw;
+                    if (cx.own_x && (FAST || (q >= cx.y0 && q < cx.y1)))
+                        *reinterpret_cast<float4*>(cx.next + (size_t)q * cx.pitch) = nw;
+                }
+                if (!FAST && s == s_top) {  // global top edge row of the same level (corners kept)
+                    const float4 e = edge_row(nw, a, cx.neg_r, cx.has_left, cx.has_right);
+                    if (s + 1 < T)
+                        W[sn][sa] = e;
+                    else if (cx.own_x && cx.y0 == 0)
+                        *reinterpret_cast<float4*>(cx.next) = e;
+                }
+            } else if (!FAST && s == s_bot && q >= cx.rs + 1) {  // global bottom edge row
+                const float4 inner = (s + 1 < T) ? W[sn][sa] : out_prev;
+                const float4 e = edge_row(inner, W[s][sm], cx.neg_r, cx.has_left, cx.has_right);
+                if (s + 1 < T)
+                    W[sn][sm] = e;
+                else if (cx.own_x && q >= cx.y0 && q < cx.y1)
+                    *reinterpret_cast<float4*>(cx.next + (size_t)q * cx.pitch) = e;
+            }
+        }
+    }
+}
+
+template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS>
+__global__ void __launch_bounds__(256) k_jacobi_stream(Geom g, RelaxBatch batch, StreamPlan plan) {
+    constexpr int HALO = halo_of(T);
+    constexpr int RS = RHS_REGS ? rs_of(T) : 3;  // unroll factor of the row loop
+    constexpr int RINGR = ring_r_of(T, RHS_REGS);
+    constexpr int NRH = RHS_REGS ? RS : 1;
+    extern __shared__ float4 smem[];
+
+    const int lane = threadIdx.x & 31;
+    const int warp_in_cta = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int gw = blockIdx.x * warps_per_cta + warp_in_cta;
+    const int strip = gw % plan.strips;
+    const int chunk = gw / plan.strips;
+    if (chunk >= plan.chunks) return;  // whole warp leaves; there is no block-wide barrier
+
+    const RelaxField& fld = batch.f[blockIdx.y];
+    Ctx cx;
+    cx.coef = fld.coef;
+    cx.neg_c = (fld.kind == F2D_BND_OPPOSITE_HORIZONTAL);
+    cx.neg_r = (fld.kind == F2D_BND_OPPOSITE_VERTICAL);
+    cx.pitch = g.pitch;
+
+    // ---- columns of this lane
+    const int jb = strip * plan.bw - HALO + 4 * lane;
+    const bool in_dom = (jb >= 0) && (jb + 3 < g.cols);
+    cx.has_left = (jb == 0);
+    cx.has_right = (jb + 3 == g.cols - 1);
+    cx.edge_warp = __any_sync(0xffffffffu, cx.has_left || cx.has_right) != 0;
+    cx.own_x = in_dom && (lane >= HALO / 4) && (lane < kLanes - HALO / 4);
+    cx.cp_bytes = in_dom ? 16 : 0;
+    const int jsafe = in_dom ? jb : 0;
+    cx.prev = PIN_ZERO ? nullptr : fld.prev + jsafe;
+    cx.rhs = fld.rhs + jsafe;
+    cx.next = fld.next + jsafe;
+    cx.ring_p = smem + (size_t)warp_in_cta * (kRingP + RINGR) * kLanes + lane;
+    cx.ring_r = cx.ring_p + kRingP * kLanes;
+
+    // ---- rows of this warp (local row indices)
+    cx.y0 = chunk * plan.chunk_rows;
+    cx.y1 = min(g.rows, cx.y0 + plan.chunk_rows);
+    cx.rs = max(0, cx.y0 - T);
+    cx.re = min(g.rows - 1, cx.y1 - 1 + T);
+    cx.top_dom = (cx.rs == 0) && (g.grow0 == 0);
+    cx.bot_dom = (cx.re == g.rows - 1) && (g.grow0 + g.rows == g.grows);
+    const int nsteps = (cx.y1 - 1 + T) - cx.rs + 1;
+    // absolute rows r for which every level is strictly inside the chunk and the stored row is owned
+    const int fast_lo = max(cx.rs + T + 1 + (cx.top_dom ? 1 : 0), cx.y0 + T);
+    const int fast_hi = cx.re;
+
+    float4 W[T][3];
+    float4 RH[NRH];
+    float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < T; ++s)
+#pragma unroll
+        for (int m = 0; m < 3; ++m) W[s][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int m = 0; m < NRH; ++m) RH[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // ---- prologue: rows rs .. rs+PFD-1 in flight
+#pragma unroll
+    for (int p = 0; p < kPFD; ++p) {
+        const int rl = cx.rs + p;
+        if (rl <= cx.re) {
+            const size_t off = (size_t)rl * cx.pitch;
+            if (!PIN_ZERO) cp_async16(cx.ring_p + (rl & (kRingP - 1)) * kLanes, cx.prev + off, cx.cp_bytes);
+            cp_async16(cx.ring_r + (rl & (RINGR - 1)) * kLanes, cx.rhs + off, cx.cp_bytes);
+        }
+        cp_async_commit();
+    }
+
+    for (int rb = 0; rb < nsteps; rb += RS) {
+        const int r_first = cx.rs + rb;
+        if (r_first >= fast_lo && r_first + RS - 1 <= fast_hi)
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev);
+        else
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev);
+    }
+    cp_async_wait<0>();
+}
+
+template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS>
+void launch_one(const Geom& g, const RelaxBatch& b, const StreamPlan& plan, int warps_per_cta, cudaStream_t st) {
+    auto kern = k_jacobi_stream<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS>;
+    const size_t smem = (size_t)warps_per_cta * (kRingP + ring_r_of(T, RHS_REGS)) * kLanes * sizeof(float4);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int total_warps = plan.strips * plan.chunks;
+    dim3 grid((total_warps + warps_per_cta - 1) / warps_per_cta, b.n);
+    kern<<<grid, warps_per_cta * 32, smem, st>>>(g, b, plan);
+}
+
+template <int T, bool RHS_REGS>
+void launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, const StreamPlan& plan, int wpc,
+              cudaStream_t st) {
+    if (!diffuse) {
+        if (b.f[0].prev == nullptr)
+            launch_one<T, false, F2D_DIV_F64, true, RHS_REGS>(g, b, plan, wpc, st);
+        else
+            launch_one<T, false, F2D_DIV_F64, false, RHS_REGS>(g, b, plan, wpc, st);
+    } else if (divmode == F2D_DIV_F64) {
+        launch_one<T, true, F2D_DIV_F64, false, RHS_REGS>(g, b, plan, wpc, st);
+    } else {
+        launch_one<T, true, F2D_DIV_F32_CORR, false, RHS_REGS>(g, b, plan, wpc, st);
+    }
+}
+
+}  // namespace
+
+bool stream_supported(const Geom& g, int T) {
+    if (T != 1 && T != 2 && T != 4 && T != 8) return false;
+    return g.cols >= 4 && (g.cols % 4 == 0) && (g.pitch % 4 == 0) && g.rows >= 3;
+}
+
+void launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
+                          const StreamTuning& tune, int sm_count, cudaStream_t st) {
+    (void)sweeps;  // == T: the step driver decomposes K into passes of 8/4/2/1 sweeps
+    StreamPlan plan;
+    plan.bw = kStripFloats - 2 * halo_of(T);
+    plan.strips = (g.cols + plan.bw - 1) / plan.bw;
+    int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
+    wpc = min(wpc, 8);
+    int chunk_rows = tune.chunk_rows;
+    if (chunk_rows <= 0) {
+        // one wave of ~10 resident warps per SM, but keep the warm-up overhead (2T redundant rows
+        // per chunk) bounded: at least 8T output rows per chunk
+        const int target_warps = sm_count * 10;
+        int chunks = max(1, target_warps / (plan.strips * b.n));
+        chunk_rows = (g.rows + chunks - 1) / chunks;
+        chunk_rows = max(chunk_rows, 8 * T);
+    }
+    chunk_rows = min(chunk_rows, g.rows);
+    plan.chunk_rows = chunk_rows;
+    plan.chunks = (g.rows + chunk_rows - 1) / chunk_rows;
+    const bool rr = (tune.rhs_in_smem == 0);
+    switch (T) {
+        case 1: rr ? launch_T<1, true>(g, b, diffuse, divmode, plan, wpc, st) : launch_T<1, false>(g, b, diffuse, divmode, plan, wpc, st); break;
+        case 2: rr ? launch_T<2, true>(g, b, diffuse, divmode, plan, wpc, st) : launch_T<2, false>(g, b, diffuse, divmode, plan, wpc, st); break;
+        case 4: rr ? launch_T<4, true>(g, b, diffuse, divmode, plan, wpc, st) : launch_T<4, false>(g, b, diffuse, divmode, plan, wpc, st); break;
+        default: rr ? launch_T<8, true>(g, b, diffuse, divmode, plan, wpc, st) : launch_T<8, false>(g, b, diffuse, divmode, plan, wpc, st); break;
+    }
+}
+
+}  // namespace f2d

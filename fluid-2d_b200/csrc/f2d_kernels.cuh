@@ -1,0 +1,58 @@
+// f2d_kernels.cuh -- launcher declarations shared by the step driver (f2d_solver.cu).
+#pragma once
+#include "f2d_common.cuh"
+
+namespace f2d {
+
+constexpr int kMaxBatch = 3;  // density, u, v relaxed in one launch
+
+// One relaxation problem: next = relax(prev, rhs) with its boundary kind.
+struct RelaxField {
+    const float* prev;  // iterate k   (nullptr: identically zero -- first pressure pass)
+    const float* rhs;   // x0 (diffuse) or divergence (pressure)
+    float* next;        // iterate k + sweeps
+    int kind;           // F2D_BND_*
+    DiffuseCoef coef;   // diffuse only
+};
+struct RelaxBatch {
+    RelaxField f[kMaxBatch];
+    int n;
+};
+
+struct AddSourceBatch {
+    float* f[kMaxBatch];
+    const float* s[kMaxBatch];
+    int n;
+};
+
+// ---- simple one-pass kernels (f2d_kernels_simple.cu) -------------------------------------
+void launch_add_sources(const Geom& g, const AddSourceBatch& b, float dt, cudaStream_t st);
+void launch_jacobi_naive(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, cudaStream_t st);
+void launch_divergence(const Geom& g, const float* u, const float* v, float* div, float h, cudaStream_t st);
+void launch_gradient(const Geom& g, const float* p, const float* u_in, const float* v_in, float* u_out,
+                     float* v_out, float h, cudaStream_t st);
+void launch_advect_velocity(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out,
+                            float dt0, cudaStream_t st);
+// forward scatter of `src` by (u,v) into `out` (must be zeroed); rows [own_begin, own_end) are the
+// source rows this slab owns.  *oob_flag (device int) is set if a target row left the local slab.
+void launch_scatter_density(const Geom& g, const float* src, const float* u, const float* v, float* out,
+                            float dt0, int own_begin, int own_end, int* oob_flag, cudaStream_t st);
+// out = smooth(set_bnd_continuous(in)) on the interior, edges = set_bnd_continuous(in), corners = in
+// (do_smooth == false: interior copied; i.e. an out-of-place set_bnd_continuous)
+void launch_smooth_bnd(const Geom& g, const float* in, float* out, bool do_smooth, cudaStream_t st);
+void launch_smooth_plain(const Geom& g, const float* in, float* out, cudaStream_t st);
+void launch_set_bnd_inplace(const Geom& g, float* f, int kind, cudaStream_t st);
+
+// ---- temporally blocked streaming relaxation (f2d_jacobi_stream.cu) ------------------------
+struct StreamTuning {
+    int chunk_rows;     // output rows per warp (0 = auto)
+    int warps_per_cta;  // 0 = auto
+    int rhs_in_smem;    // 0 = rhs rows ride in a register ring (default), 1 = re-read from the smem ring
+};
+// `sweeps` (1..T) Jacobi sweeps in one pass over the field(s); returns false if (T, geometry)
+// is not supported by the streaming kernel.
+bool stream_supported(const Geom& g, int T);
+void launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
+                          const StreamTuning& tune, int sm_count, cudaStream_t st);
+
+}  // namespace f2d

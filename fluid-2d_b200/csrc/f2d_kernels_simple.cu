@@ -1,0 +1,269 @@
+// f2d_kernels_simple.cu -- the one-pass stages of the stable-fluids step for sm_100a.
+//
+// Each kernel is one thread per cell over the FULL local field (edges included) and produces
+// its own boundary cells (see classify_cell), so no separate set_boundary launches and no
+// full-field copies are needed (the reference issues 94 + 94 of them per step,
+// SURVEY.md Appendix C).  All kernels are out-of-place unless noted.
+#include "f2d_kernels.cuh"
+
+namespace f2d {
+
+namespace {
+constexpr int kBx = 32, kBy = 8;
+inline dim3 grid2d(const Geom& g, int z = 1) { return dim3((g.cols + kBx - 1) / kBx, (g.rows + kBy - 1) / kBy, z); }
+#define F2D_CELL_IJ()                                   \
+    const int j = blockIdx.x * kBx + threadIdx.x;       \
+    const int i = blockIdx.y * kBy + threadIdx.y;       \
+    if (i >= g.rows || j >= g.cols) return;
+}  // namespace
+
+// ---------------------------------------------------------------------------- add_sources
+// add_sources_kernel (src/fluid_solver_gpu.cu:56-67): f = FFMA(dt, s, f) on the global interior,
+// in place, no boundary pass.  Up to three fields per launch (blockIdx.z).
+__global__ void __launch_bounds__(kBx* kBy) k_add_sources(Geom g, AddSourceBatch b, float dt) {
+    F2D_CELL_IJ();
+    const int gi = g.grow0 + i;
+    if (gi < 1 || gi > g.grows - 2 || j < 1 || j > g.cols - 2) return;
+    const size_t o = (size_t)i * g.pitch + j;
+    float* f = b.f[blockIdx.z];
+    f[o] = __fmaf_rn(dt, __ldg(b.s[blockIdx.z] + o), f[o]);
+}
+
+void launch_add_sources(const Geom& g, const AddSourceBatch& b, float dt, cudaStream_t st) {
+    k_add_sources<<<grid2d(g, b.n), dim3(kBx, kBy), 0, st>>>(g, b, dt);
+}
+
+// --------------------------------------------------------------------------- naive Jacobi
+// One sweep of diffuse_iteration_kernel (gpu.cu:69-85) or p_iteration_kernel (gpu.cu:179-191)
+// with the boundary pass fused; ping-pong buffers replace the reference's per-iteration
+// full-field copy (gpu.cu:302, :380).  Bring-up / cross-check path (F2D_JACOBI_NAIVE).
+template <bool DIFFUSE, int DIVMODE>
+__global__ void __launch_bounds__(kBx* kBy) k_jacobi_naive(Geom g, RelaxBatch b) {
+    F2D_CELL_IJ();
+    const RelaxField& fld = b.f[blockIdx.z];
+    const CellSrc c = classify_cell(g, i, j, fld.kind);
+    const size_t o = (size_t)i * g.pitch + j;
+    const float* __restrict__ prev = fld.prev;
+    if (c.cls == CELL_KEEP) {
+        fld.next[o] = prev ? prev[o] : 0.0f;
+        return;
+    }
+    const size_t so = (size_t)c.si * g.pitch + c.sj;
+    float W = 0.f, E = 0.f, N = 0.f, S = 0.f;
+    if (prev) {
+        W = prev[so - 1];
+        E = prev[so + 1];
+        N = prev[so - g.pitch];
+        S = prev[so + g.pitch];
+    }
+    const float r = __ldg(fld.rhs + so);
+    float val;
+    if (DIFFUSE)
+        val = diffuse_update<DIVMODE>(W, E, N, S, r, fld.coef);
+    else
+        val = pressure_update(r, E, W, S, N);
+    fld.next[o] = apply_sign(val, c.negate);
+}
+
+void launch_jacobi_naive(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, cudaStream_t st) {
+    dim3 gr = grid2d(g, b.n), bl(kBx, kBy);
+    if (!diffuse)
+        k_jacobi_naive<false, F2D_DIV_F64><<<gr, bl, 0, st>>>(g, b);
+    else if (divmode == F2D_DIV_F64)
+        k_jacobi_naive<true, F2D_DIV_F64><<<gr, bl, 0, st>>>(g, b);
+    else
+        k_jacobi_naive<true, F2D_DIV_F32_CORR><<<gr, bl, 0, st>>>(g, b);
+}
+
+// ----------------------------------------------------------------------------- divergence
+// calculate_divergence_kernel (gpu.cu:164-177) + set_boundary_continuous (gpu.cu:376); corners are
+// the zeros of the reference's memset (gpu.cu:363).
+__global__ void __launch_bounds__(kBx* kBy) k_divergence(Geom g, const float* __restrict__ u,
+                                                        const float* __restrict__ v, float* __restrict__ dv,
+                                                        float mhalf_h) {
+    F2D_CELL_IJ();
+    const CellSrc c = classify_cell(g, i, j, F2D_BND_CONTINUOUS);
+    const size_t o = (size_t)i * g.pitch + j;
+    if (c.cls == CELL_KEEP) {
+        dv[o] = 0.0f;
+        return;
+    }
+    const size_t so = (size_t)c.si * g.pitch + c.sj;
+    dv[o] = divergence_update(u[so + 1], u[so - 1], v[so + g.pitch], v[so - g.pitch], mhalf_h);
+}
+
+void launch_divergence(const Geom& g, const float* u, const float* v, float* dv, float h, cudaStream_t st) {
+    k_divergence<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u, v, dv, -0.5f * h);
+}
+
+// ------------------------------------------------------------------------------- gradient
+// remove_p_kernel (gpu.cu:193-206) + set_boundary_opposite_horizontal(u) / _vertical(v)
+// (gpu.cu:402-403).  Out of place so that edge threads can re-evaluate their inward neighbour.
+__global__ void __launch_bounds__(kBx* kBy) k_gradient(Geom g, const float* __restrict__ p,
+                                                      const float* __restrict__ u_in,
+                                                      const float* __restrict__ v_in, float* __restrict__ u_out,
+                                                      float* __restrict__ v_out, float h) {
+    F2D_CELL_IJ();
+    // u and v have different boundary kinds but the same source cell
+    const CellSrc cu = classify_cell(g, i, j, F2D_BND_OPPOSITE_HORIZONTAL);
+    const CellSrc cv = classify_cell(g, i, j, F2D_BND_OPPOSITE_VERTICAL);
+    const size_t o = (size_t)i * g.pitch + j;
+    if (cu.cls == CELL_KEEP) {
+        u_out[o] = u_in[o];
+        v_out[o] = v_in[o];
+        return;
+    }
+    const size_t so = (size_t)cu.si * g.pitch + cu.sj;
+    const float un = gradient_update(u_in[so], p[so + 1], p[so - 1], h);
+    const float vn = gradient_update(v_in[so], p[so + g.pitch], p[so - g.pitch], h);
+    u_out[o] = apply_sign(un, cu.negate);
+    v_out[o] = apply_sign(vn, cv.negate);
+}
+
+void launch_gradient(const Geom& g, const float* p, const float* u_in, const float* v_in, float* u_out,
+                     float* v_out, float h, cudaStream_t st) {
+    k_gradient<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, p, u_in, v_in, u_out, v_out, h);
+}
+
+// ------------------------------------------------------------------------ advect (gather)
+// advect_kernel (gpu.cu:99-129) for u AND v in one pass: both are advected by the same (U0,V0)
+// (gpu.cu:248-251), so the back-traced point and the bilinear weights are shared.  The gathers go
+// through the read-only path; with CFL-bounded displacements they hit L1/L2.  Global row indices
+// are used for y so that a row slab rounds exactly like the single-GPU run.
+__global__ void __launch_bounds__(kBx* kBy) k_advect_velocity(Geom g, const float* __restrict__ u0,
+                                                             const float* __restrict__ v0,
+                                                             float* __restrict__ u_out, float* __restrict__ v_out,
+                                                             float dt0) {
+    F2D_CELL_IJ();
+    const CellSrc cu = classify_cell(g, i, j, F2D_BND_OPPOSITE_HORIZONTAL);
+    const CellSrc cv = classify_cell(g, i, j, F2D_BND_OPPOSITE_VERTICAL);
+    const size_t o = (size_t)i * g.pitch + j;
+    if (cu.cls == CELL_KEEP) {
+        u_out[o] = u0[o];
+        v_out[o] = v0[o];
+        return;
+    }
+    const size_t so = (size_t)cu.si * g.pitch + cu.sj;
+    float x = __fmaf_rn(-__ldg(u0 + so), dt0, (float)cu.sj);
+    float y = __fmaf_rn(-__ldg(v0 + so), dt0, (float)(g.grow0 + cu.si));
+    x = fmaxf(1.5f, fminf((float)g.cols - 1.5f, x));
+    y = fmaxf(1.5f, fminf((float)g.grows - 1.5f, y));
+    const Bilinear b = bilinear_setup(x, y);
+    // local row of the gather; a slab's halo is sized from the CFL bound, clamp defensively
+    int li0 = b.i0 - g.grow0;
+    li0 = max(0, min(g.rows - 2, li0));
+    const size_t a = (size_t)li0 * g.pitch + b.j0;
+    const float un = bilinear_gather(b, __ldg(u0 + a), __ldg(u0 + a + 1), __ldg(u0 + a + g.pitch), __ldg(u0 + a + g.pitch + 1));
+    const float vn = bilinear_gather(b, __ldg(v0 + a), __ldg(v0 + a + 1), __ldg(v0 + a + g.pitch), __ldg(v0 + a + g.pitch + 1));
+    u_out[o] = apply_sign(un, cu.negate);
+    v_out[o] = apply_sign(vn, cv.negate);
+}
+
+void launch_advect_velocity(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out,
+                            float dt0, cudaStream_t st) {
+    k_advect_velocity<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u0, v0, u_out, v_out, dt0);
+}
+
+// ----------------------------------------------------------------------- advect (scatter)
+// advect_trace_kernel (gpu.cu:131-162): forward trace of every interior cell and a bilinear splat
+// with four float atomics (RED.ADD.F32, flush-to-zero like the reference's).  `out` is zeroed by
+// the caller (gpu.cu:337).  The boundary pass of gpu.cu:355 is fused into launch_smooth_bnd.
+__global__ void __launch_bounds__(kBx* kBy) k_scatter_density(Geom g, const float* __restrict__ src,
+                                                             const float* __restrict__ u,
+                                                             const float* __restrict__ v, float* out, float dt0,
+                                                             int own_begin, int own_end, int* oob_flag) {
+    F2D_CELL_IJ();
+    const int gi = g.grow0 + i;
+    if (i < own_begin || i >= own_end || gi < 1 || gi > g.grows - 2 || j < 1 || j > g.cols - 2) return;
+    const size_t o = (size_t)i * g.pitch + j;
+    const float x = __fmaf_rn(__ldg(u + o), dt0, (float)j);
+    const float y = __fmaf_rn(__ldg(v + o), dt0, (float)gi);
+    if (x < 0.5f || x > (float)g.cols - 1.5f || y < 0.5f || y > (float)g.grows - 1.5f) return;
+    const Bilinear b = bilinear_setup(x, y);
+    const int li0 = b.i0 - g.grow0;
+    if (li0 < 0 || li0 + 1 >= g.rows) {  // displacement exceeded the slab halo: report, never fault
+        *oob_flag = 1;
+        return;
+    }
+    const float val = __ldg(src + o);
+    float* t = out + (size_t)li0 * g.pitch + b.j0;
+    atomicAdd(t, __fmul_rn(__fmul_rn(b.s1, b.s3), val));
+    atomicAdd(t + g.pitch, __fmul_rn(__fmul_rn(b.s1, b.s2), val));
+    atomicAdd(t + 1, __fmul_rn(__fmul_rn(b.s0, b.s3), val));
+    atomicAdd(t + g.pitch + 1, __fmul_rn(__fmul_rn(b.s0, b.s2), val));
+}
+
+void launch_scatter_density(const Geom& g, const float* src, const float* u, const float* v, float* out,
+                            float dt0, int own_begin, int own_end, int* oob_flag, cudaStream_t st) {
+    k_scatter_density<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, src, u, v, out, dt0, own_begin, own_end, oob_flag);
+}
+
+// ------------------------------------------------------------------- smooth + boundary pass
+// set_boundary_continuous after the scatter (gpu.cu:355) fused with smooth_kernel (gpu.cu:87-97,
+// no boundary pass afterwards, gpu.cu:314-323).  B(in) denotes `in` after the boundary pass:
+// edge cells read their inward neighbour, everything else reads itself.
+__device__ __forceinline__ float bnd_read(const Geom& g, const float* __restrict__ in, int i, int j) {
+    const CellSrc c = classify_cell(g, i, j, F2D_BND_CONTINUOUS);
+    return __ldg(in + (size_t)c.si * g.pitch + c.sj);  // CELL_KEEP has (si,sj) == (i,j)
+}
+
+template <bool SMOOTH>
+__global__ void __launch_bounds__(kBx* kBy) k_smooth_bnd(Geom g, const float* __restrict__ in, float* __restrict__ out) {
+    F2D_CELL_IJ();
+    const int gi = g.grow0 + i;
+    const size_t o = (size_t)i * g.pitch + j;
+    const bool interior = gi >= 1 && gi <= g.grows - 2 && j >= 1 && j <= g.cols - 2 && i >= 1 && i <= g.rows - 2;
+    if (!SMOOTH || !interior) {
+        out[o] = bnd_read(g, in, i, j);
+        return;
+    }
+    out[o] = smooth_update(__ldg(in + o), bnd_read(g, in, i, j - 1), bnd_read(g, in, i, j + 1),
+                           bnd_read(g, in, i - 1, j), bnd_read(g, in, i + 1, j));
+}
+
+void launch_smooth_bnd(const Geom& g, const float* in, float* out, bool do_smooth, cudaStream_t st) {
+    if (do_smooth)
+        k_smooth_bnd<true><<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, in, out);
+    else
+        k_smooth_bnd<false><<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, in, out);
+}
+
+// smooth_kernel exactly as a stand-alone stage (gpu.cu:87-97): interior only, edges untouched.
+__global__ void __launch_bounds__(kBx* kBy) k_smooth_plain(Geom g, const float* __restrict__ in, float* __restrict__ out) {
+    F2D_CELL_IJ();
+    const int gi = g.grow0 + i;
+    if (gi < 1 || gi > g.grows - 2 || j < 1 || j > g.cols - 2 || i < 1 || i > g.rows - 2) return;
+    const size_t o = (size_t)i * g.pitch + j;
+    out[o] = smooth_update(in[o], in[o - 1], in[o + 1], in[o - g.pitch], in[o + g.pitch]);
+}
+
+void launch_smooth_plain(const Geom& g, const float* in, float* out, cudaStream_t st) {
+    k_smooth_plain<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, in, out);
+}
+
+// --------------------------------------------------------------------- in-place set_bnd
+// set_boundary_*_kernel (gpu.cu:11-54) as a stand-alone stage (parity tests, f2d_stage_set_bnd).
+__global__ void k_set_bnd_inplace(Geom g, float* f, int kind) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool neg_c = (kind == F2D_BND_OPPOSITE_HORIZONTAL), neg_r = (kind == F2D_BND_OPPOSITE_VERTICAL);
+    if (m < g.rows) {  // left / right columns of every local row that is a global interior row
+        const int gi = g.grow0 + m;
+        if (gi >= 1 && gi <= g.grows - 2) {
+            float* r = f + (size_t)m * g.pitch;
+            r[0] = apply_sign(r[1], neg_c);
+            r[g.cols - 1] = apply_sign(r[g.cols - 2], neg_c);
+        }
+    }
+    if (m >= 1 && m <= g.cols - 2) {  // global top / bottom rows, corners excluded
+        if (g.grow0 == 0) f[m] = apply_sign(f[g.pitch + m], neg_r);
+        if (g.grow0 + g.rows == g.grows)
+            f[(size_t)(g.rows - 1) * g.pitch + m] = apply_sign(f[(size_t)(g.rows - 2) * g.pitch + m], neg_r);
+    }
+}
+
+void launch_set_bnd_inplace(const Geom& g, float* f, int kind, cudaStream_t st) {
+    const int n = max(g.rows, g.cols);
+    k_set_bnd_inplace<<<(n + 127) / 128, 128, 0, st>>>(g, f, kind);
+}
+
+}  // namespace f2d

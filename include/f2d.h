@@ -1,0 +1,163 @@
+/*
+ * f2d.h -- C ABI of the B200-native stable-fluids step (libf2d.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of mworchel/fluid-2d:
+ * fluid_solver::solve (src/fluid_solver.hpp:16-24) and the stages behind it
+ * (src/fluid_solver_gpu.cu:222-404).  Plain pointers and sizes only; no C++,
+ * CUDA or torch types cross this boundary.  Every entry point returns an int
+ * status (F2D_OK == 0); f2d_last_error() describes the last failure of the
+ * calling thread.  Nothing throws.  One f2d_solver may be used by one thread at
+ * a time (the reference solver is not re-entrant either: member temp buffers,
+ * src/fluid_solver_gpu.cuh:62-68).
+ *
+ * Arithmetic contract: the results follow fluid_solver_gpu (true Jacobi, edges
+ * without corners, density `smooth`); iteration counts
+ * are parameters instead of the literals 15/20 (src/fluid_solver_gpu.cu:238-252).
+ *
+ * The C++ adapter `fluid_solver_b200` (include/fluid_solver_b200.hpp) and the
+ * Python host mirror (fluid-2d_b200/solver.py) are thin layers over these calls.
+ */
+#ifndef F2D_H_
+#define F2D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F2D_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define F2D_API __attribute__((visibility("default")))
+#else
+#define F2D_API
+#endif
+
+/* status codes */
+#define F2D_OK 0
+#define F2D_ERR_INVALID 1   /* bad argument / configuration                  */
+#define F2D_ERR_CUDA 2      /* a CUDA runtime call failed (see last_error)   */
+#define F2D_ERR_NO_DEVICE 3 /* no usable CUDA device: there is NO CPU fallback */
+#define F2D_ERR_STATE 4     /* call not valid in the solver's current state  */
+
+/* fields of the solver state (replace the reference's m_*_buffer members,
+ * src/fluid_solver_gpu.cuh:62-68) */
+#define F2D_FIELD_DENSITY 0
+#define F2D_FIELD_U 1 /* horizontal velocity */
+#define F2D_FIELD_V 2 /* vertical velocity   */
+#define F2D_FIELD_DENSITY_SOURCE 3
+#define F2D_FIELD_U_SOURCE 4
+#define F2D_FIELD_V_SOURCE 5
+#define F2D_FIELD_PRESSURE 6   /* last pressure of the last project (debug/parity) */
+#define F2D_FIELD_DIVERGENCE 7 /* last divergence of the last project             */
+#define F2D_FIELD_COUNT 8
+
+/* boundary kinds (src/fluid_solver_gpu.cu:11-54) */
+#define F2D_BND_CONTINUOUS 0
+#define F2D_BND_OPPOSITE_HORIZONTAL 1
+#define F2D_BND_OPPOSITE_VERTICAL 2
+
+/* relaxation kernels */
+#define F2D_JACOBI_NAIVE 0  /* one sweep per launch, one thread per cell (bring-up / cross-check) */
+#define F2D_JACOBI_STREAM 1 /* register-pipelined, temporally blocked row streaming (default)     */
+
+/* how the diffuse sweep forms (x0 + a*sum4) / (1 + 4a)  (src/fluid_solver_gpu.cu:81-82) */
+#define F2D_DIV_F64 0      /* (float)((double)num / (1.0 + 4.0*a)): the reference's own arithmetic */
+#define F2D_DIV_F32_CORR 1 /* fp32 reciprocal + two-term FMA residual correction (default)          */
+
+typedef struct f2d_solver f2d_solver; /* opaque: owns device fields, stream, graphs */
+
+typedef struct f2d_config {
+    uint32_t struct_size;    /* sizeof(f2d_config), for ABI evolution                          */
+    uint32_t rows, cols;     /* LOCAL field extent held by this solver (== global on one GPU)   */
+    uint32_t diffuse_iters;  /* Kd; fluid_solver_gpu::solve uses 15 (gpu.cu:238,245-246)        */
+    uint32_t project_iters;  /* Kp; fluid_solver_gpu::solve uses 20 (gpu.cu:247,252)            */
+    uint32_t smooth;         /* 1 = density smooth after advect as gpu.cu:240 (default)         */
+    uint32_t jacobi_mode;    /* F2D_JACOBI_*                                                    */
+    uint32_t temporal_block; /* sweeps fused per kernel pass (1,2,4,8); 0 = auto                */
+    uint32_t divide_mode;    /* F2D_DIV_*                                                       */
+    uint32_t use_graph;      /* 1 = capture the step into a CUDA graph (default)                */
+    int32_t device;          /* CUDA device ordinal; -1 = current device                        */
+    /* row-slab decomposition (multi-GPU).  One GPU: global_rows = rows, row_offset = 0, halo = 0.
+     * Local row i is global row row_offset + i; rows [0,halo) and [rows-halo,rows) are halo rows
+     * owned by the neighbour slabs unless they touch the global top/bottom edge.               */
+    uint32_t global_rows;
+    uint32_t row_offset;
+    uint32_t halo;
+    uint32_t reserved0;
+    void* stream; /* cudaStream_t to run on; NULL = the solver creates its own                  */
+} f2d_config;
+
+/* Fill *cfg with defaults for a rows x cols single-GPU solver (Kd=15, Kp=20, smooth=1: exactly
+ * fluid_solver_gpu::solve). */
+F2D_API int f2d_config_default(f2d_config* cfg, uint32_t rows, uint32_t cols);
+
+/* fluid_solver_gpu::fluid_solver_gpu(rows, cols)  (src/fluid_solver_gpu.cu:209-218): allocate all
+ * device fields once.  Fails with F2D_ERR_NO_DEVICE when no GPU is present. */
+F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out);
+F2D_API void f2d_destroy(f2d_solver* s);
+
+/* ---- the reference interface ------------------------------------------------------------
+ * fluid_solver::solve (src/fluid_solver.hpp:16-24; GPU: src/fluid_solver_gpu.cu:222-258):
+ * host arrays (row-major, pitch == cols, like grid<float>::data()), density/u/v updated in
+ * place, sources const.  Upload -> one device step -> download; blocking. */
+F2D_API int f2d_solve_host(f2d_solver* s, float* density, const float* density_source, float diffusion_rate,
+                   float* u, float* v, const float* u_source, const float* v_source, float viscosity,
+                   float dt);
+
+/* ---- device-resident extension (the per-call PCIe copies are the interface's tax) -------- */
+/* copy(m_*_buffer, grid)  (src/utilities.hpp:57-59).  NULL pointers are skipped. */
+F2D_API int f2d_upload(f2d_solver* s, const float* density, const float* u, const float* v);
+F2D_API int f2d_set_sources(f2d_solver* s, const float* density_source, const float* u_source,
+                    const float* v_source);
+/* copy(grid, m_*_buffer)  (src/utilities.hpp:65-67) */
+F2D_API int f2d_download(f2d_solver* s, float* density, float* u, float* v);
+/* generic single-field transfer; host pitch == cols */
+F2D_API int f2d_upload_field(f2d_solver* s, int field, const float* host);
+F2D_API int f2d_download_field(f2d_solver* s, int field, float* host);
+/* simulation::update zeroes the sources after each solve (src/simulation.cpp:62-64) */
+F2D_API int f2d_clear_sources(f2d_solver* s);
+
+/* `nsteps` solve() steps on the device-resident state with constant sources; asynchronous on the
+ * solver's stream. */
+F2D_API int f2d_step(f2d_solver* s, float diffusion_rate, float viscosity, float dt, uint32_t nsteps);
+/* same, bracketed by CUDA events on the solver's stream; blocks; *elapsed_ms = device time */
+F2D_API int f2d_step_timed(f2d_solver* s, float diffusion_rate, float viscosity, float dt, uint32_t nsteps,
+                   float* elapsed_ms);
+F2D_API int f2d_sync(f2d_solver* s);
+
+/* ---- single stages on the device-resident state (parity tests; each mirrors one private
+ * method of fluid_solver_gpu, src/fluid_solver_gpu.cuh:27-56) ------------------------------- */
+F2D_API int f2d_stage_set_bnd(f2d_solver* s, int field, int kind);           /* gpu.cu:260-276 */
+F2D_API int f2d_stage_add_sources(f2d_solver* s, int field, float dt);       /* gpu.cu:278-288; field d/u/v, its own source */
+F2D_API int f2d_stage_diffuse(f2d_solver* s, int field, int kind, float rate, float dt, uint32_t iters); /* gpu.cu:290-312 */
+F2D_API int f2d_stage_smooth(f2d_solver* s);                                  /* gpu.cu:314-323 (density) */
+F2D_API int f2d_stage_advect_density(f2d_solver* s, float dt);                /* gpu.cu:325-356, trace=true, by current u,v */
+F2D_API int f2d_stage_advect_velocity(f2d_solver* s, float dt);               /* gpu.cu:248-251: U0,V0 <- u,v; advect u; advect v */
+F2D_API int f2d_stage_project(f2d_solver* s, uint32_t iters);                 /* gpu.cu:358-404 */
+
+/* ---- measurement helpers -------------------------------------------------------------------
+ * Run `reps` pressure-relaxation solves of `iters` Jacobi sweeps each on scratch fields with the
+ * configured kernel and return the device time of all of them (CUDA events on the solver stream).
+ * Used by bench.py for the "Jacobi HBM GB/s vs peak" roofline line. */
+F2D_API int f2d_bench_jacobi(f2d_solver* s, int diffuse_like, uint32_t iters, uint32_t reps, float* elapsed_ms);
+/* number of kernel launches (graph kernel nodes included) issued by this solver so far */
+F2D_API int f2d_launch_count(const f2d_solver* s, uint64_t* launches);
+
+/* ---- interop ------------------------------------------------------------------------------- */
+/* device pointer + pitch (in floats) of a state field, for zero-copy views (torch, NCCL halos) */
+F2D_API int f2d_field_ptr(f2d_solver* s, int field, void** device_ptr, size_t* pitch_elems);
+F2D_API int f2d_get_config(const f2d_solver* s, f2d_config* out);
+/* the stream the solver launches on (cudaStream_t as void*) */
+F2D_API int f2d_get_stream(const f2d_solver* s, void** stream);
+
+F2D_API const char* f2d_last_error(void);
+F2D_API int f2d_abi_version(void);
+F2D_API int f2d_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F2D_H_ */
