@@ -1,0 +1,130 @@
+"""Multi-GPU leg of bench.py: one process per GPU (torchrun), row slabs, NCCL halo exchange.
+value = N^2 * steps / max-over-ranks(device time); strong scaling on the 16384^2 grid."""
+import json
+import os
+import time
+
+import numpy as np
+
+from bench import DIFFUSION_RATE, DT, METRIC, UNIT, VISCOSITY, ClockSampler, measured_peaks, step_bytes
+
+
+def canonical_rows(n, r0, r1):
+    """Rows [r0, r1) of the canonical fields, generated locally (no full-grid host arrays)."""
+    import ctypes as C
+
+    from oracle import sfo
+
+    L = sfo.lib()
+    rows = r1 - r0
+    arrs = [np.empty((rows, n), dtype=np.float32) for _ in range(6)]
+    fp = C.POINTER(C.c_float)
+    # sfo_canonical_fields indexes the FULL field: pass pointers shifted back by r0 rows
+    ptrs = [C.cast(a.ctypes.data - r0 * n * 4, fp) for a in arrs]
+    import threading
+
+    nthr = min(16, os.cpu_count() or 1, max(1, rows // 256))
+    bounds = np.linspace(r0, r1, nthr + 1).astype(int)
+    ts = [threading.Thread(target=L.sfo_canonical_fields, args=(n, int(bounds[k]), int(bounds[k + 1]), *ptrs)) for k in range(nthr)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return arrs
+
+
+def run_multi_gpu(args, workload):
+    import torch
+    import torch.distributed as dist
+
+    import fluid2d_b200 as f2d
+    from fluid2d_b200 import slab as slabmod
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world != args.gpus:
+        raise SystemExit("launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n, kd, kp = workload["n"], workload["kd"], workload["kp"]
+    halo = int(os.environ.get("F2D_HALO", "32"))
+    cfl = 8
+    sl = slabmod.partition(n, world, halo, rank)
+    uid = slabmod.broadcast_unique_id(dist, rank, device=torch.device("cuda", local_rank))
+    solver = slabmod.make_slab_solver(sl, n, uid, cfl_cells=cfl, device=local_rank, diffuse_iters=kd, project_iters=kp)
+    cfg = solver.config()
+    d, u, v, sd, su, sv = canonical_rows(n, sl.row_offset, sl.row_offset + sl.rows)
+    solver.upload(d, u, v)
+    solver.set_sources(sd, su, sv)
+
+    def barrier():
+        solver.sync()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    solver.step(DIFFUSION_RATE, VISCOSITY, DT, args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    l0, x0 = solver.launch_count(), slabmod.comm_exchanges(solver)
+    ms = solver.step_timed(DIFFUSION_RATE, VISCOSITY, DT, args.steps)
+    barrier()
+    launches, xch = solver.launch_count() - l0, slabmod.comm_exchanges(solver) - x0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end: every rank uploads its slab from pinned host memory, steps once, downloads it
+    pins = [torch.from_numpy(a).pin_memory() for a in (d, u, v, sd, su, sv)]
+    hd, hu, hv, hsd, hsu, hsv = [p.numpy() for p in pins]
+    e2e_steps = 3
+    for _ in range(1):
+        solver.solve(hd, hsd, DIFFUSION_RATE, hu, hv, hsu, hsv, VISCOSITY, DT)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        solver.solve(hd, hsd, DIFFUSION_RATE, hu, hv, hsu, hsv, VISCOSITY, DT)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    solver.close()
+
+    if rank == 0:
+        cells = float(n) * n
+        value = cells * args.steps / (ms_max * 1e-3)
+        peak, peak_src = measured_peaks()
+        bps = step_bytes(kd, kp)
+        halo_bytes = xch / max(1, args.steps) * halo * n * 4  # per neighbour per direction per step (<= 3 fields/exchange)
+        from bench import cpu_reference_solver, canonical
+
+        run, kind = cpu_reference_solver()
+        cpu_t = run(canonical(2048), kd, kp)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": workload["scaling"],
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload["name"], "grid": [n, n], "diffuse_iters": kd, "project_iters": kp,
+                       "parallelism": "row slabs x%d, halo %d rows, NCCL send/recv in the step graph" % (world, halo),
+                       "temporal_block": int(cfg.temporal_block), "jacobi_mode": int(cfg.jacobi_mode),
+                       "divide_mode": int(cfg.divide_mode), "cfl_cells": cfl,
+                       "l2": "inputs larger than L2 (slab fields of %.0f MiB)" % (sl.rows * n * 4 / 2**20)},
+            "roofline": {"bound": "hbm", "kernel": "whole step, algorithmic bytes (SURVEY 8d)", "achieved": bps * value / 1e9,
+                         "peak": peak * world, "unit": "GB/s", "frac": bps * value / 1e9 / (peak * world), "traffic": None,
+                         "peak_source": peak_src + " x n_gpus",
+                         "halo": {"exchanges_per_step": xch / max(1, args.steps), "rows": halo,
+                                  "approx_bytes_per_neighbour_per_step": halo_bytes}},
+            "cpu_baseline": {"value": 2048 * 2048 / cpu_t, "unit": UNIT, "cores": 1, "kind": kind,
+                             "sample": "1 step of a 2048x2048 grid, Kd=Kp=%d, fluid_solver_cpu (1 thread)" % kd},
+            "e2e": {"value": cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(6 * 4 * cells),
+                    "d2h_bytes_per_step": int(3 * 4 * cells), "steps": e2e_steps,
+                    "api": "FluidSolverB200.solve per slab (pinned host slabs, halo rows included)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()

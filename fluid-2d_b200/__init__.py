@@ -36,6 +36,7 @@ from .capi import (  # noqa: F401
     lib_path,
     load,
 )
+from . import slab  # noqa: F401
 from .solver import FluidSolverB200  # noqa: F401
 
 __all__ = ["FluidSolverB200", "SolverConfig", "F2DError", "build", "load", "device_count"]

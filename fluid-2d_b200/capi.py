@@ -112,6 +112,9 @@ def load():
         "f2d_field_ptr": [vp, i32, C.POINTER(vp), C.POINTER(C.c_size_t)],
         "f2d_get_config": [vp, cfgp],
         "f2d_get_stream": [vp, C.POINTER(vp)],
+        "f2d_comm_unique_id": [C.c_char_p],
+        "f2d_comm_init": [vp, C.c_char_p, i32, i32, i32],
+        "f2d_comm_stats": [vp, C.POINTER(C.c_uint64)],
         "f2d_abi_version": [],
         "f2d_device_count": [],
     }

@@ -54,7 +54,7 @@ __host__ __device__ constexpr int ring_r_of(int T, bool rhs_regs) {
 }
 
 struct StreamPlan {
-    int strips, chunks, chunk_rows, bw;
+    int strips, chunks, chunk_rows, bw, edge_trim;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
@@ -62,6 +62,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src,
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void st_global_f4(float* p, const float4& v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
@@ -113,13 +116,19 @@ struct Ctx {
 
 // RS consecutive row steps starting at relative row rb (a multiple of RS, so rb % 3 == 0 and the
 // register slots of every row are compile-time constants).
+//
+// FAST blocks run every level unconditionally.  During the warm-up / drain of a chunk some levels
+// then work on rows outside the chunk's input range (garbage, but finite): those results only ever
+// feed cells outside the dependency cone of the rows this warp stores, and the store itself is
+// predicated on the owned row range.  Only blocks in which a level meets a GLOBAL top or bottom edge
+// row (edge rule, corner carry) take the checked path (FAST == false).
 template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS, bool FAST, int RS, int RINGR, int NRH>
 __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, float4 (&W)[T][3], float4 (&RH)[NRH],
                                           float4& out_prev) {
 #pragma unroll
     for (int k = 0; k < RS; ++k) {
         const int rr = rb + k;
-        if (!FAST && rr >= nsteps) break;
+        if (rr >= nsteps) break;
         const int r = cx.rs + rr;
 
         // 1. keep PFD rows in flight
@@ -134,7 +143,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
         }
         // 2. row r has landed (each lane reads back only the 16 bytes it copied itself)
         cp_async_wait<kPFD>();
-        if (FAST || r <= cx.re) {
+        if (FAST || r <= cx.re) {  // FAST: past the last input row this re-reads a stale ring slot (harmless)
             if (!PIN_ZERO)
                 W[0][m3(k)] = cx.ring_p[(r & (kRingP - 1)) * kLanes];
             else
@@ -142,7 +151,18 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
             if (RHS_REGS) RH[mrs(k, RS)] = cx.ring_r[(r & (RINGR - 1)) * kLanes];
         }
 
-        // 3. level s+1 produces row q = r - s - 1 from level s rows q-1, q, q+1.
+        // 3. west/east neighbours of the centre rows of ALL levels: those rows were produced in the
+        //    previous step, so the 2T shuffles are issued up front and their latency overlaps the
+        //    arithmetic of the lower levels
+        float wl[T], er[T];
+#pragma unroll
+        for (int s = 0; s < T; ++s) {
+            const float4 b = W[s][m3(k - s - 1)];
+            wl[s] = __shfl_up_sync(0xffffffffu, b.w, 1);
+            er[s] = __shfl_down_sync(0xffffffffu, b.x, 1);
+        }
+
+        // 4. level s+1 produces row q = r - s - 1 from level s rows q-1, q, q+1.
         //    active levels: rs+1 <= q <= re-1  <=>  s_lo <= s <= s_hi
         const int s_lo = r - cx.re, s_hi = r - cx.rs - 2;
         const int s_top = cx.top_dom ? r - 2 : -1;           // level whose q == 1 (global top edge above it)
@@ -154,8 +174,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
             const int sn = (s + 1 < T) ? s + 1 : 0;  // keeps the dead branch's index in range
             if (FAST || (s >= s_lo && s <= s_hi)) {
                 const float4 a = W[s][sa], b = W[s][sm], c = W[s][sc];
-                const float l = __shfl_up_sync(0xffffffffu, b.w, 1);
-                const float rt = __shfl_down_sync(0xffffffffu, b.x, 1);
+                const float l = wl[s], rt = er[s];
                 float4 rhs;
                 if (RHS_REGS)
                     rhs = RH[mrs(k - s - 1, RS)];
@@ -171,15 +190,14 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
                     W[sn][sm] = nw;
                 } else {
                     out_prev = nw;
-                    if (cx.own_x && (FAST || (q >= cx.y0 && q < cx.y1)))
-                        *reinterpret_cast<float4*>(cx.next + (size_t)q * cx.pitch) = nw;
+                    if (cx.own_x && q >= cx.y0 && q < cx.y1) st_global_f4(cx.next + (size_t)q * cx.pitch, nw);
                 }
                 if (!FAST && s == s_top) {  // global top edge row of the same level (corners kept)
                     const float4 e = edge_row(nw, a, cx.neg_r, cx.has_left, cx.has_right);
                     if (s + 1 < T)
                         W[sn][sa] = e;
                     else if (cx.own_x && cx.y0 == 0)
-                        *reinterpret_cast<float4*>(cx.next) = e;
+                        st_global_f4(cx.next, e);
                 }
             } else if (!FAST && s == s_bot && q >= cx.rs + 1) {  // global bottom edge row
                 const float4 inner = (s + 1 < T) ? W[sn][sa] : out_prev;
@@ -187,7 +205,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
                 if (s + 1 < T)
                     W[sn][sm] = e;
                 else if (cx.own_x && q >= cx.y0 && q < cx.y1)
-                    *reinterpret_cast<float4*>(cx.next + (size_t)q * cx.pitch) = e;
+                    st_global_f4(cx.next + (size_t)q * cx.pitch, e);
             }
         }
     }
@@ -232,16 +250,25 @@ __global__ void __launch_bounds__(256) k_jacobi_stream(Geom g, RelaxBatch batch,
     cx.ring_r = cx.ring_p + kRingP * kLanes;
 
     // ---- rows of this warp (local row indices)
-    cx.y0 = chunk * plan.chunk_rows;
-    cx.y1 = min(g.rows, cx.y0 + plan.chunk_rows);
-    cx.rs = max(0, cx.y0 - T);
+    // the first / last chunk are `edge_trim` rows shorter: their edge-rule steps cost more
+    cx.y0 = (chunk == 0) ? 0 : chunk * plan.chunk_rows - plan.edge_trim;
+    cx.y1 = (chunk == plan.chunks - 1) ? g.rows : (chunk + 1) * plan.chunk_rows - plan.edge_trim;
+    // T warm-up rows above the first owned row; a chunk that owns only the global bottom edge row
+    // must warm up for row rows-2, which the edge rule copies from
+    cx.rs = max(0, min(cx.y0, g.rows - 2) - T);
     cx.re = min(g.rows - 1, cx.y1 - 1 + T);
+    // pin the per-warp constants in registers: without this the compiler re-derives them every row
+    // from the (dynamically indexed) kernel-parameter bank
+    asm volatile("" : "+l"(cx.prev), "+l"(cx.rhs), "+l"(cx.next));
+    asm volatile("" : "+r"(cx.pitch), "+r"(cx.rs), "+r"(cx.re), "+r"(cx.y0), "+r"(cx.y1), "+r"(cx.cp_bytes));
     cx.top_dom = (cx.rs == 0) && (g.grow0 == 0);
     cx.bot_dom = (cx.re == g.rows - 1) && (g.grow0 + g.rows == g.grows);
     const int nsteps = (cx.y1 - 1 + T) - cx.rs + 1;
-    // absolute rows r for which every level is strictly inside the chunk and the stored row is owned
-    const int fast_lo = max(cx.rs + T + 1 + (cx.top_dom ? 1 : 0), cx.y0 + T);
-    const int fast_hi = cx.re;
+    // absolute input rows r during which some level meets a global edge row:
+    //   top:    q == 1 at level s+1  <=>  r = s + 2,      s in [0, T)
+    //   bottom: q == re at level s+1 <=>  r = re + s + 1, s in [0, T)
+    const int top_lo = cx.top_dom ? 2 : 1 << 30, top_hi = cx.top_dom ? T + 1 : -1;
+    const int bot_lo = cx.bot_dom ? cx.re + 1 : 1 << 30, bot_hi = cx.bot_dom ? cx.re + T : -1;
 
     float4 W[T][3];
     float4 RH[NRH];
@@ -266,8 +293,9 @@ __global__ void __launch_bounds__(256) k_jacobi_stream(Geom g, RelaxBatch batch,
     }
 
     for (int rb = 0; rb < nsteps; rb += RS) {
-        const int r_first = cx.rs + rb;
-        if (r_first >= fast_lo && r_first + RS - 1 <= fast_hi)
+        const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
+        const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
+        if (!edge_block)
             run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev);
         else
             run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev);
@@ -275,28 +303,64 @@ __global__ void __launch_bounds__(256) k_jacobi_stream(Geom g, RelaxBatch batch,
     cp_async_wait<0>();
 }
 
+// One wave, every resident warp slot busy: the chunk height is chosen so that the number of CTAs is
+// the largest value <= (CTAs resident per SM) x (SM count); all warps then run concurrently and finish
+// together.  At least 4T output rows per chunk bound the warm-up redundancy on small grids.
 template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS>
-void launch_one(const Geom& g, const RelaxBatch& b, const StreamPlan& plan, int warps_per_cta, cudaStream_t st) {
+void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, int sm_count, cudaStream_t st) {
     auto kern = k_jacobi_stream<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS>;
-    const size_t smem = (size_t)warps_per_cta * (kRingP + ring_r_of(T, RHS_REGS)) * kLanes * sizeof(float4);
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
+    wpc = min(wpc, 8);
+    const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS)) * kLanes * sizeof(float4);
+    static int occ_cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (occ_cache[wpc] == 0) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem) != cudaSuccess || occ < 1) occ = 1;
+        occ_cache[wpc] = occ;
+    }
+    StreamPlan plan;
+    plan.bw = kStripFloats - 2 * halo_of(T);
+    plan.strips = (g.cols + plan.bw - 1) / plan.bw;
+    int chunk_rows = tune.chunk_rows;
+    int trim = (g.grow0 == 0 && g.grow0 + g.rows == g.grows) ? 4 * T + 2 : 0;  // both global edges in this field
+    if (chunk_rows <= 0) {
+        const long warp_slots = (long)occ_cache[wpc] * sm_count * wpc;
+        long chunks = warp_slots / ((long)plan.strips * b.n);
+        if (chunks < 1) chunks = 1;
+        if (chunks < 3) trim = 0;
+        chunk_rows = (int)((g.rows + 2 * trim + chunks - 1) / chunks);
+        if (chunk_rows < 4 * T) {
+            chunk_rows = 4 * T;
+            trim = 0;
+        }
+    } else {
+        trim = 0;
+    }
+    chunk_rows = min(chunk_rows, g.rows);
+    if (chunk_rows < 2 * trim + 2) trim = 0;
+    plan.chunk_rows = chunk_rows;
+    plan.edge_trim = trim;
+    plan.chunks = (g.rows + 2 * trim + chunk_rows - 1) / chunk_rows;
+    while (plan.chunks > 1 && (plan.chunks - 1) * chunk_rows - trim >= g.rows) --plan.chunks;
+    if (plan.chunks == 1) plan.edge_trim = 0;
     const int total_warps = plan.strips * plan.chunks;
-    dim3 grid((total_warps + warps_per_cta - 1) / warps_per_cta, b.n);
-    kern<<<grid, warps_per_cta * 32, smem, st>>>(g, b, plan);
+    dim3 grid((total_warps + wpc - 1) / wpc, b.n);
+    kern<<<grid, wpc * 32, smem, st>>>(g, b, plan);
 }
 
 template <int T, bool RHS_REGS>
-void launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, const StreamPlan& plan, int wpc,
+void launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, const StreamTuning& tune, int sm_count,
               cudaStream_t st) {
     if (!diffuse) {
         if (b.f[0].prev == nullptr)
-            launch_one<T, false, F2D_DIV_F64, true, RHS_REGS>(g, b, plan, wpc, st);
+            launch_one<T, false, F2D_DIV_F64, true, RHS_REGS>(g, b, tune, sm_count, st);
         else
-            launch_one<T, false, F2D_DIV_F64, false, RHS_REGS>(g, b, plan, wpc, st);
+            launch_one<T, false, F2D_DIV_F64, false, RHS_REGS>(g, b, tune, sm_count, st);
     } else if (divmode == F2D_DIV_F64) {
-        launch_one<T, true, F2D_DIV_F64, false, RHS_REGS>(g, b, plan, wpc, st);
+        launch_one<T, true, F2D_DIV_F64, false, RHS_REGS>(g, b, tune, sm_count, st);
     } else {
-        launch_one<T, true, F2D_DIV_F32_CORR, false, RHS_REGS>(g, b, plan, wpc, st);
+        launch_one<T, true, F2D_DIV_F32_CORR, false, RHS_REGS>(g, b, tune, sm_count, st);
     }
 }
 
@@ -310,29 +374,14 @@ bool stream_supported(const Geom& g, int T) {
 void launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
                           const StreamTuning& tune, int sm_count, cudaStream_t st) {
     (void)sweeps;  // == T: the step driver decomposes K into passes of 8/4/2/1 sweeps
-    StreamPlan plan;
-    plan.bw = kStripFloats - 2 * halo_of(T);
-    plan.strips = (g.cols + plan.bw - 1) / plan.bw;
-    int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
-    wpc = min(wpc, 8);
-    int chunk_rows = tune.chunk_rows;
-    if (chunk_rows <= 0) {
-        // one wave of ~10 resident warps per SM, but keep the warm-up overhead (2T redundant rows
-        // per chunk) bounded: at least 8T output rows per chunk
-        const int target_warps = sm_count * 10;
-        int chunks = max(1, target_warps / (plan.strips * b.n));
-        chunk_rows = (g.rows + chunks - 1) / chunks;
-        chunk_rows = max(chunk_rows, 8 * T);
-    }
-    chunk_rows = min(chunk_rows, g.rows);
-    plan.chunk_rows = chunk_rows;
-    plan.chunks = (g.rows + chunk_rows - 1) / chunk_rows;
-    const bool rr = (tune.rhs_in_smem == 0);
+    // T = 8 keeps the right-hand side in the smem ring (unroll 3): with a register ring the unrolled
+    // row loop (9 x 8 levels) outgrows the instruction cache
+    const bool rr = (tune.rhs_in_smem == 0) && T < 8;
     switch (T) {
-        case 1: rr ? launch_T<1, true>(g, b, diffuse, divmode, plan, wpc, st) : launch_T<1, false>(g, b, diffuse, divmode, plan, wpc, st); break;
-        case 2: rr ? launch_T<2, true>(g, b, diffuse, divmode, plan, wpc, st) : launch_T<2, false>(g, b, diffuse, divmode, plan, wpc, st); break;
-        case 4: rr ? launch_T<4, true>(g, b, diffuse, divmode, plan, wpc, st) : launch_T<4, false>(g, b, diffuse, divmode, plan, wpc, st); break;
-        default: rr ? launch_T<8, true>(g, b, diffuse, divmode, plan, wpc, st) : launch_T<8, false>(g, b, diffuse, divmode, plan, wpc, st); break;
+        case 1: rr ? launch_T<1, true>(g, b, diffuse, divmode, tune, sm_count, st) : launch_T<1, false>(g, b, diffuse, divmode, tune, sm_count, st); break;
+        case 2: rr ? launch_T<2, true>(g, b, diffuse, divmode, tune, sm_count, st) : launch_T<2, false>(g, b, diffuse, divmode, tune, sm_count, st); break;
+        case 4: rr ? launch_T<4, true>(g, b, diffuse, divmode, tune, sm_count, st) : launch_T<4, false>(g, b, diffuse, divmode, tune, sm_count, st); break;
+        default: launch_T<8, false>(g, b, diffuse, divmode, tune, sm_count, st); break;
     }
 }
 

@@ -20,8 +20,9 @@ struct RelaxBatch {
 };
 
 struct AddSourceBatch {
-    float* f[kMaxBatch];
-    const float* s[kMaxBatch];
+    const float* f[kMaxBatch];  // field
+    float* o[kMaxBatch];        // destination (may alias f: in place)
+    const float* s[kMaxBatch];  // source
     int n;
 };
 
@@ -32,7 +33,8 @@ void launch_divergence(const Geom& g, const float* u, const float* v, float* div
 void launch_gradient(const Geom& g, const float* p, const float* u_in, const float* v_in, float* u_out,
                      float* v_out, float h, cudaStream_t st);
 void launch_advect_velocity(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out,
-                            float dt0, cudaStream_t st);
+                            float dt0, int own_begin, int own_end, int* oob_flag, cudaStream_t st);
+void launch_add_rows(const Geom& g, float* f, int row0, int nrows, const float* src, cudaStream_t st);
 // forward scatter of `src` by (u,v) into `out` (must be zeroed); rows [own_begin, own_end) are the
 // source rows this slab owns.  *oob_flag (device int) is set if a target row left the local slab.
 void launch_scatter_density(const Geom& g, const float* src, const float* u, const float* v, float* out,

@@ -18,15 +18,20 @@ inline dim3 grid2d(const Geom& g, int z = 1) { return dim3((g.cols + kBx - 1) / 
 }  // namespace
 
 // ---------------------------------------------------------------------------- add_sources
-// add_sources_kernel (src/fluid_solver_gpu.cu:56-67): f = FFMA(dt, s, f) on the global interior,
-// in place, no boundary pass.  Up to three fields per launch (blockIdx.z).
+// add_sources_kernel (src/fluid_solver_gpu.cu:56-67): o = FFMA(dt, s, f) on the global interior, no
+// boundary pass; every other cell is passed through, so the destination may be the field itself
+// (in place) or a fresh buffer.  Up to three fields per launch (blockIdx.z).
 __global__ void __launch_bounds__(kBx* kBy) k_add_sources(Geom g, AddSourceBatch b, float dt) {
     F2D_CELL_IJ();
     const int gi = g.grow0 + i;
-    if (gi < 1 || gi > g.grows - 2 || j < 1 || j > g.cols - 2) return;
     const size_t o = (size_t)i * g.pitch + j;
-    float* f = b.f[blockIdx.z];
-    f[o] = __fmaf_rn(dt, __ldg(b.s[blockIdx.z] + o), f[o]);
+    const float* f = b.f[blockIdx.z];
+    float* out = b.o[blockIdx.z];
+    const bool interior = !(gi < 1 || gi > g.grows - 2 || j < 1 || j > g.cols - 2);
+    if (interior)
+        out[o] = __fmaf_rn(dt, __ldg(b.s[blockIdx.z] + o), f[o]);
+    else if (out != f)
+        out[o] = f[o];
 }
 
 void launch_add_sources(const Geom& g, const AddSourceBatch& b, float dt, cudaStream_t st) {
@@ -133,7 +138,7 @@ void launch_gradient(const Geom& g, const float* p, const float* u_in, const flo
 __global__ void __launch_bounds__(kBx* kBy) k_advect_velocity(Geom g, const float* __restrict__ u0,
                                                              const float* __restrict__ v0,
                                                              float* __restrict__ u_out, float* __restrict__ v_out,
-                                                             float dt0) {
+                                                             float dt0, int own_begin, int own_end, int* oob_flag) {
     F2D_CELL_IJ();
     const CellSrc cu = classify_cell(g, i, j, F2D_BND_OPPOSITE_HORIZONTAL);
     const CellSrc cv = classify_cell(g, i, j, F2D_BND_OPPOSITE_VERTICAL);
@@ -151,6 +156,7 @@ __global__ void __launch_bounds__(kBx* kBy) k_advect_velocity(Geom g, const floa
     const Bilinear b = bilinear_setup(x, y);
     // local row of the gather; a slab's halo is sized from the CFL bound, clamp defensively
     int li0 = b.i0 - g.grow0;
+    if ((li0 < 0 || li0 > g.rows - 2) && i >= own_begin && i < own_end) *oob_flag = 1;  // CFL promise broken
     li0 = max(0, min(g.rows - 2, li0));
     const size_t a = (size_t)li0 * g.pitch + b.j0;
     const float un = bilinear_gather(b, __ldg(u0 + a), __ldg(u0 + a + 1), __ldg(u0 + a + g.pitch), __ldg(u0 + a + g.pitch + 1));
@@ -160,8 +166,27 @@ __global__ void __launch_bounds__(kBx* kBy) k_advect_velocity(Geom g, const floa
 }
 
 void launch_advect_velocity(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out,
-                            float dt0, cudaStream_t st) {
-    k_advect_velocity<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u0, v0, u_out, v_out, dt0);
+                            float dt0, int own_begin, int own_end, int* oob_flag, cudaStream_t st) {
+    k_advect_velocity<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u0, v0, u_out, v_out, dt0, own_begin, own_end, oob_flag);
+}
+
+// rows [row0, row0 + nrows) of f += src (src is a dense nrows x pitch block): the receiving end of the
+// reverse halo exchange of the density scatter (multi-GPU)
+__global__ void k_add_rows(float* __restrict__ f, const float* __restrict__ src, size_t n4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = reinterpret_cast<float4*>(f)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x = __fadd_rn(a.x, b.x);
+    a.y = __fadd_rn(a.y, b.y);
+    a.z = __fadd_rn(a.z, b.z);
+    a.w = __fadd_rn(a.w, b.w);
+    reinterpret_cast<float4*>(f)[i] = a;
+}
+
+void launch_add_rows(const Geom& g, float* f, int row0, int nrows, const float* src, cudaStream_t st) {
+    const size_t n4 = (size_t)nrows * g.pitch / 4;
+    k_add_rows<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(f + (size_t)row0 * g.pitch, src, n4);
 }
 
 // ----------------------------------------------------------------------- advect (scatter)

@@ -15,8 +15,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
+#include <initializer_list>
 #include <new>
+#include <utility>
 #include <vector>
+
+#include <dlfcn.h>
 
 #include "f2d_kernels.cuh"
 
@@ -123,6 +128,54 @@ struct f2d_solver {
     // ---- building blocks -----------------------------------------------------------------
     void count(int n = 1) { launches += (uint64_t)n; }
 
+    // ---- row-slab halo bookkeeping (multi-GPU) -------------------------------------------
+    // A slab holds `halo` rows of its neighbours on each slab-internal side.  Every stencil
+    // stage is evaluated on ALL local rows; rows closer than the stage radius to a slab-internal
+    // edge come out wrong ("invalid").  inv(buf) = number of invalid rows at the slab-internal
+    // edges of buf (0 right after an exchange).  A stage with radius r maps inv -> inv + r and is
+    // legal while the result stays <= halo (owned rows valid); otherwise its inputs are
+    // exchanged first.  One GPU: no neighbours, nothing to do.
+    void* comm = nullptr;  // ncclComm_t
+    int rank = 0, nranks = 1;
+    int cfl_cells = 8;     // bound on the advection displacement per step, in cells (caller's promise)
+    float *rx_up = nullptr, *rx_down = nullptr;  // landing zones of the reverse (scatter) exchange
+    uint64_t exchanges = 0, exchanges_in_graph = 0;
+    std::vector<std::pair<const float*, int>> inv_table;
+
+    bool multi() const { return comm != nullptr; }
+    int H() const { return (int)cfg.halo; }
+    bool has_up() const { return g.grow0 > 0; }
+    bool has_down() const { return g.grow0 + g.rows < g.grows; }
+    int get_inv(const float* p) const {
+        for (auto& e : inv_table)
+            if (e.first == p) return e.second;
+        return 0;
+    }
+    void set_inv(const float* p, int v) {
+        if (!multi() || !p) return;
+        for (auto& e : inv_table)
+            if (e.first == p) {
+                e.second = v;
+                return;
+            }
+        inv_table.emplace_back(p, v);
+    }
+    int exchange(const float* const* bufs, int n);             // forward halo exchange, inv := 0
+    int reverse_exchange_add(float* buf);                      // halo partial sums -> owner, added
+    // make sure inv(buf) <= limit for every listed buffer, exchanging the offenders in one group
+    int need(std::initializer_list<std::pair<const float*, int>> reqs) {
+        if (!multi()) return F2D_OK;
+        const float* todo[8];
+        int n = 0;
+        for (auto& r : reqs) {
+            if (!r.first || get_inv(r.first) <= r.second) continue;
+            bool dup = false;
+            for (int i = 0; i < n; ++i) dup |= (todo[i] == r.first);
+            if (!dup && n < 8) todo[n++] = r.first;
+        }
+        return n ? exchange(todo, n) : F2D_OK;
+    }
+
     // K relaxation sweeps for n problems.  in[i] == nullptr means a zero start (pressure).
     // out[i] receives the buffer holding the final iterate: a pool buffer the caller must
     // release, or in[i] itself when K == 0.
@@ -152,11 +205,35 @@ struct f2d_solver {
         const bool stream_mode = (cfg.jacobi_mode == F2D_JACOBI_STREAM);
         uint32_t left = K;
         int flip = 0;
+        if (multi()) {
+            // the right-hand side is read by every pass: refresh its halos once, up front, together
+            // with any start iterate that is not fully valid
+            const float* todo[2 * kMaxBatch];
+            int m = 0;
+            for (int i = 0; i < n; ++i) {
+                if (get_inv(rhs[i]) > 0) todo[m++] = rhs[i];
+                if (cur[i] && cur[i] != rhs[i] && get_inv(cur[i]) > 0) todo[m++] = cur[i];
+            }
+            if (m) F2D_TRY(exchange(todo, m));
+        }
         while (left > 0) {
             uint32_t T = 1;
             if (stream_mode) {
                 T = cfg.temporal_block;
                 while (T > left) T >>= 1;
+            }
+            if (multi()) {
+                // a pass of T sweeps: inv(next) = max(inv(prev) + T, inv(rhs) + T - 1) must stay <= halo
+                if ((int)T > H()) return fail(F2D_ERR_INVALID, "halo (%d) shallower than temporal_block (%u)", H(), T);
+                const float* todo[2 * kMaxBatch];
+                int m = 0;
+                for (int i = 0; i < n; ++i) {
+                    const bool xp = cur[i] && get_inv(cur[i]) + (int)T > H();
+                    const bool xr = get_inv(rhs[i]) + (int)T - 1 > H();
+                    if (xp) todo[m++] = cur[i];
+                    if (xr && !(xp && rhs[i] == cur[i])) todo[m++] = rhs[i];
+                }
+                if (m) F2D_TRY(exchange(todo, m));
             }
             RelaxBatch b;
             b.n = n;
@@ -172,7 +249,11 @@ struct f2d_solver {
             else
                 launch_jacobi_naive(g, b, diffuse, (int)cfg.divide_mode, stream);
             count();
-            for (int i = 0; i < n; ++i) cur[i] = b.f[i].next;
+            for (int i = 0; i < n; ++i) {
+                const int ip = cur[i] ? get_inv(cur[i]) : 0;
+                set_inv(b.f[i].next, std::max(ip + (int)T, get_inv(rhs[i]) + (int)T - 1));
+                cur[i] = b.f[i].next;
+            }
             flip ^= 1;
             left -= T;
         }
@@ -191,15 +272,20 @@ struct f2d_solver {
         last_div = last_p = nullptr;
         float* dv = acquire();
         if (!dv) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        F2D_TRY(need({{u_in, H() - 1}, {v_in, H() - 1}}));  // radius-1 stencil
         launch_divergence(g, u_in, v_in, dv, h(), stream);
         count();
+        set_inv(dv, std::max(get_inv(u_in), get_inv(v_in)) + 1);
         const float* pin[1] = {nullptr};
         const float* prhs[1] = {dv};
         const int kind[1] = {F2D_BND_CONTINUOUS};
         const float* pout[1];
         F2D_TRY(relax(1, pin, prhs, kind, nullptr, false, K, pout));
+        F2D_TRY(need({{pout[0], H() - 1}}));
         launch_gradient(g, pout[0], u_in, v_in, u_out, v_out, h(), stream);
         count();
+        set_inv(u_out, std::max(get_inv(pout[0]) + 1, std::max(get_inv(u_in), get_inv(v_in))));
+        set_inv(v_out, get_inv(u_out));
         F2D_CUDA(cudaGetLastError());
         // keep p / div alive as debug views until the next project
         last_div = dv;
@@ -210,61 +296,86 @@ struct f2d_solver {
     // One full solve() step on the device-resident state (order of gpu.cu:236-252).
     int enqueue_step(float diffusion_rate, float viscosity, float dt) {
         float *d = state[F2D_FIELD_DENSITY], *u = state[F2D_FIELD_U], *v = state[F2D_FIELD_V];
-        // ---------------- density chain (uses the PRE-step u, v) ----------------
+        if (multi()) {
+            // assume nothing about the halos on entry (only owned rows valid), so that the exchange
+            // schedule baked into a captured graph is right for every replay
+            inv_table.clear();
+            set_inv(d, H());
+            set_inv(u, H());
+            set_inv(v, H());
+            if (cfl_cells + 1 > H()) return fail(F2D_ERR_INVALID, "halo (%d) shallower than the advection radius (%d)", H(), cfl_cells + 1);
+        }
+        // ---- add_sources for all three fields in one launch (gpu.cu:237, :243-244).  u and v get
+        //      their sources OUT of place: the density scatter below still needs the pre-step u, v
+        //      (the reference runs the whole density chain first, gpu.cu:236-240).
+        float *us = acquire(), *vs = acquire();
+        if (!us || !vs) return fail(F2D_ERR_STATE, "scratch pool exhausted");
         {
             AddSourceBatch ab;
-            ab.n = 1;
+            ab.n = 3;
             ab.f[0] = d;
+            ab.o[0] = d;
             ab.s[0] = state[F2D_FIELD_DENSITY_SOURCE];
-            launch_add_sources(g, ab, dt, stream);  // gpu.cu:237
+            ab.f[1] = u;
+            ab.o[1] = us;
+            ab.s[1] = state[F2D_FIELD_U_SOURCE];
+            ab.f[2] = v;
+            ab.o[2] = vs;
+            ab.s[2] = state[F2D_FIELD_V_SOURCE];
+            launch_add_sources(g, ab, dt, stream);
             count();
-            const float* in[1] = {d};
-            const float* rhs[1] = {d};  // x0 == the field after add_sources (gpu.cu:300)
-            const int kind[1] = {F2D_BND_CONTINUOUS};
-            const DiffuseCoef kc[1] = {diffuse_coef(diffusion_rate, dt)};
-            const float* dd[1];
-            F2D_TRY(relax(1, in, rhs, kind, kc, true, cfg.diffuse_iters, dd));  // gpu.cu:238
+            set_inv(us, get_inv(u));  // pointwise: halo validity carries over
+            set_inv(vs, get_inv(v));
+        }
+        // ---- diffuse d, u, v in one batch (gpu.cu:238, :245-246): x0 == the field after add_sources
+        const float* dif[3];
+        {
+            const float* in[3] = {d, us, vs};
+            const float* rhs[3] = {d, us, vs};
+            const int kind[3] = {F2D_BND_CONTINUOUS, F2D_BND_OPPOSITE_HORIZONTAL, F2D_BND_OPPOSITE_VERTICAL};
+            const DiffuseCoef kc[3] = {diffuse_coef(diffusion_rate, dt), diffuse_coef(viscosity, dt), diffuse_coef(viscosity, dt)};
+            F2D_TRY(relax(3, in, rhs, kind, kc, true, cfg.diffuse_iters, dif));
+        }
+        // ---- density: forward scatter by the PRE-step (u, v), boundary pass + smooth (gpu.cu:239-240)
+        {
             float* sc = acquire();
             if (!sc) return fail(F2D_ERR_STATE, "scratch pool exhausted");
             F2D_CUDA(cudaMemsetAsync(sc, 0, field_bytes, stream));  // gpu.cu:337
-            launch_scatter_density(g, dd[0], u, v, sc, dt0(dt), own_begin(), own_end(), oob_flag, stream);  // gpu.cu:239
+            launch_scatter_density(g, dif[0], u, v, sc, dt0(dt), own_begin(), own_end(), oob_flag, stream);
             count();
-            if (dd[0] != d) release(dd[0]);
+            if (dif[0] != d) release(dif[0]);
+            if (multi()) {
+                // splats that landed in halo rows belong to the neighbour slab: send them home and add,
+                // then refresh the halos for the radius-1 smooth
+                F2D_TRY(reverse_exchange_add(sc));
+                const float* one[1] = {sc};
+                F2D_TRY(exchange(one, 1));
+            }
             launch_smooth_bnd(g, sc, d, cfg.smooth != 0, stream);  // gpu.cu:355 + :240
             count();
+            set_inv(d, 1);
             release(sc);
         }
-        // ---------------- velocity chain ----------------
+        // ---- velocity: project, self-advect, project (gpu.cu:247-252)
         {
-            AddSourceBatch ab;
-            ab.n = 2;
-            ab.f[0] = u;
-            ab.s[0] = state[F2D_FIELD_U_SOURCE];
-            ab.f[1] = v;
-            ab.s[1] = state[F2D_FIELD_V_SOURCE];
-            launch_add_sources(g, ab, dt, stream);  // gpu.cu:243-244
-            count();
-            const float* in[2] = {u, v};
-            const float* rhs[2] = {u, v};
-            const int kind[2] = {F2D_BND_OPPOSITE_HORIZONTAL, F2D_BND_OPPOSITE_VERTICAL};
-            const DiffuseCoef kc[2] = {diffuse_coef(viscosity, dt), diffuse_coef(viscosity, dt)};
-            const float* uv1[2];
-            F2D_TRY(relax(2, in, rhs, kind, kc, true, cfg.diffuse_iters, uv1));  // gpu.cu:245-246
+            const float *u1 = dif[1], *v1 = dif[2];
+            if (u1 != us) {  // K > 0: the add_sources outputs are no longer needed
+                release(us);
+                release(vs);
+            }
             float *u2 = acquire(), *v2 = acquire();
             if (!u2 || !v2) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-            F2D_TRY(project(uv1[0], uv1[1], u2, v2, cfg.project_iters));  // gpu.cu:247
-            // advect both components by (U0,V0) = (u2,v2) (gpu.cu:248-251)
-            float *u3, *v3;
-            if (uv1[0] != u) {
-                u3 = const_cast<float*>(uv1[0]);
-                v3 = const_cast<float*>(uv1[1]);
-            } else {
-                u3 = acquire();
-                v3 = acquire();
-                if (!u3 || !v3) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+            F2D_TRY(project(u1, v1, u2, v2, cfg.project_iters));  // gpu.cu:247
+            // advect both components by (U0,V0) = (u2,v2) (gpu.cu:248-251); u1/v1 are free to be overwritten
+            float *u3 = const_cast<float*>(u1), *v3 = const_cast<float*>(v1);
+            {
+                const int r = cfl_cells + 1;  // gather radius: displacement bound + bilinear footprint
+                F2D_TRY(need({{u2, H() - r}, {v2, H() - r}}));
+                launch_advect_velocity(g, u2, v2, u3, v3, dt0(dt), own_begin(), own_end(), oob_flag, stream);
+                count();
+                set_inv(u3, std::max(get_inv(u2), get_inv(v2)) + r);
+                set_inv(v3, get_inv(u3));
             }
-            launch_advect_velocity(g, u2, v2, u3, v3, dt0(dt), stream);
-            count();
             release(u2);
             release(v2);
             F2D_TRY(project(u3, v3, u, v, cfg.project_iters));  // gpu.cu:252, result lands in the state buffers
@@ -291,9 +402,10 @@ struct f2d_solver {
         if (last_div) release(last_div);
         if (last_p) release(last_p);
         last_div = last_p = nullptr;
-        const uint64_t before = launches;
+        const uint64_t before = launches, xbefore = exchanges;
         cudaGraph_t graph = nullptr;
-        F2D_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        // relaxed mode: NCCL (multi-GPU) may issue its own runtime calls while we capture
+        F2D_CUDA(cudaStreamBeginCapture(stream, multi() ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
         int rc = enqueue_step(diffusion_rate, viscosity, dt);
         cudaError_t ce = cudaStreamEndCapture(stream, &graph);
         if (rc != F2D_OK) {
@@ -303,6 +415,8 @@ struct f2d_solver {
         if (ce != cudaSuccess) return fail(F2D_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
         graph_kernels = launches - before;
         launches = before;  // capture launched nothing yet
+        exchanges_in_graph = exchanges - xbefore;
+        exchanges = xbefore;
         F2D_CUDA(cudaGraphInstantiate(&graph_exec, graph, 0));
         cudaGraphDestroy(graph);
         graph_key = {diffusion_rate, viscosity, dt, true};
@@ -316,6 +430,7 @@ struct f2d_solver {
             for (uint32_t s = 0; s < nsteps; ++s) {
                 F2D_CUDA(cudaGraphLaunch(graph_exec, stream));
                 launches += graph_kernels;
+                exchanges += exchanges_in_graph;
             }
         } else {
             for (uint32_t s = 0; s < nsteps; ++s) F2D_TRY(enqueue_step(diffusion_rate, viscosity, dt));
@@ -344,8 +459,172 @@ struct f2d_solver {
     }
 };
 
+// ============================================================ halo exchange over NCCL (NVLink)
+// NCCL is resolved at run time (dlopen) so that libf2d.so has no link-time dependency on it and a
+// process that already loaded a copy (torch bundles one) shares it.  The send/recv pairs are
+// enqueued on the solver's stream, so they are captured into the step's CUDA graph like kernels.
+namespace {
+struct NcclId {
+    char internal[128];
+};
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat = 7;  // ncclFloat32 (nccl.h)
+
+int load_nccl() {
+    if (g_nccl.lib) return F2D_OK;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);  // a copy already in the process
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return fail(F2D_ERR_STATE, "cannot load libnccl.so.2: %s", dlerror());
+    auto sym = [&](const char* n) { return dlsym(lib, n); };
+    g_nccl.GetUniqueId = (int (*)(NcclId*))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))sym("ncclSend");
+    g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))sym("ncclRecv");
+    g_nccl.GroupStart = (int (*)())sym("ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart ||
+        !g_nccl.GroupEnd || !g_nccl.GetErrorString || !g_nccl.CommDestroy)
+        return fail(F2D_ERR_STATE, "libnccl.so.2 lacks a required symbol");
+    g_nccl.lib = lib;
+    return F2D_OK;
+}
+
+#define F2D_NCCL(expr)                                                                                   \
+    do {                                                                                                 \
+        int r_ = (expr);                                                                                 \
+        if (r_ != 0) return fail(F2D_ERR_CUDA, "%s failed: %s", #expr, g_nccl.GetErrorString(r_));      \
+    } while (0)
+}  // namespace
+
+// Forward exchange: my first/last `halo` OWNED rows go to the neighbours' halo rows, theirs come
+// into mine.  All listed buffers travel in one NCCL group (one fused P2P kernel over NVLink).
+int f2d_solver::exchange(const float* const* bufs, int n) {
+    if (!multi() || n == 0) return F2D_OK;
+    const size_t cnt = (size_t)H() * (size_t)g.pitch;
+    F2D_NCCL(g_nccl.GroupStart());
+    for (int i = 0; i < n; ++i) {
+        float* b = const_cast<float*>(bufs[i]);
+        if (has_up()) {
+            F2D_NCCL(g_nccl.Send(b + cnt, cnt, kNcclFloat, rank - 1, comm, stream));  // rows [H, 2H)
+            F2D_NCCL(g_nccl.Recv(b, cnt, kNcclFloat, rank - 1, comm, stream));        // rows [0, H)
+        }
+        if (has_down()) {
+            float* tail = b + (size_t)(g.rows - 2 * H()) * g.pitch;
+            F2D_NCCL(g_nccl.Send(tail, cnt, kNcclFloat, rank + 1, comm, stream));        // rows [rows-2H, rows-H)
+            F2D_NCCL(g_nccl.Recv(tail + cnt, cnt, kNcclFloat, rank + 1, comm, stream));  // rows [rows-H, rows)
+        }
+    }
+    F2D_NCCL(g_nccl.GroupEnd());
+    for (int i = 0; i < n; ++i) set_inv(bufs[i], 0);
+    ++exchanges;
+    return F2D_OK;
+}
+
+// Reverse exchange of the density scatter: the partial sums that landed in my halo rows belong to
+// the neighbour; they are sent home and added to its first/last owned rows.
+int f2d_solver::reverse_exchange_add(float* buf) {
+    if (!multi()) return F2D_OK;
+    const size_t cnt = (size_t)H() * (size_t)g.pitch;
+    F2D_NCCL(g_nccl.GroupStart());
+    if (has_up()) {
+        F2D_NCCL(g_nccl.Send(buf, cnt, kNcclFloat, rank - 1, comm, stream));
+        F2D_NCCL(g_nccl.Recv(rx_up, cnt, kNcclFloat, rank - 1, comm, stream));
+    }
+    if (has_down()) {
+        F2D_NCCL(g_nccl.Send(buf + (size_t)(g.rows - H()) * g.pitch, cnt, kNcclFloat, rank + 1, comm, stream));
+        F2D_NCCL(g_nccl.Recv(rx_down, cnt, kNcclFloat, rank + 1, comm, stream));
+    }
+    F2D_NCCL(g_nccl.GroupEnd());
+    if (has_up()) {
+        launch_add_rows(g, buf, H(), H(), rx_up, stream);
+        count();
+    }
+    if (has_down()) {
+        launch_add_rows(g, buf, g.rows - 2 * H(), H(), rx_down, stream);
+        count();
+    }
+    F2D_CUDA(cudaGetLastError());
+    ++exchanges;
+    set_inv(buf, H());
+    return F2D_OK;
+}
+
 // =============================================================================== C ABI
 extern "C" {
+
+// ---- multi-GPU bootstrap: rank 0 makes the id, the host side broadcasts it (torch.distributed),
+// every rank calls f2d_comm_init (collective).
+F2D_API int f2d_comm_unique_id(char* id128) {
+    if (!id128) return fail(F2D_ERR_INVALID, "NULL argument");
+    F2D_TRY(load_nccl());
+    NcclId id;
+    F2D_NCCL(g_nccl.GetUniqueId(&id));
+    memcpy(id128, id.internal, sizeof(id.internal));
+    return F2D_OK;
+}
+
+F2D_API int f2d_comm_init(f2d_solver* s, const char* id128, int rank, int nranks, int cfl_cells) {
+    if (!s || !id128) return fail(F2D_ERR_INVALID, "NULL argument");
+    if (nranks < 2 || rank < 0 || rank >= nranks) return fail(F2D_ERR_INVALID, "bad rank/nranks");
+    if (s->cfg.halo == 0) return fail(F2D_ERR_INVALID, "a slab solver needs halo > 0");
+    if (s->comm) return fail(F2D_ERR_STATE, "communicator already initialised");
+    if ((s->g.grow0 > 0) != (rank > 0) || (s->g.grow0 + s->g.rows < s->g.grows) != (rank < nranks - 1))
+        return fail(F2D_ERR_INVALID, "slab position does not match rank (slabs are ordered by rank)");
+    if (s->g.rows < 3 * (int)s->cfg.halo) return fail(F2D_ERR_INVALID, "slab thinner than 3 halos");
+    F2D_CUDA(cudaSetDevice(s->device));
+    F2D_TRY(load_nccl());
+    NcclId id;
+    memcpy(id.internal, id128, sizeof(id.internal));
+    void* comm = nullptr;
+    F2D_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
+    const size_t bytes = (size_t)s->cfg.halo * s->g.pitch * sizeof(float);
+    F2D_CUDA(cudaMalloc(&s->rx_up, bytes));
+    F2D_CUDA(cudaMalloc(&s->rx_down, bytes));
+    s->comm = comm;
+    s->rank = rank;
+    s->nranks = nranks;
+    s->cfl_cells = cfl_cells > 0 ? cfl_cells : 8;
+    {
+        // establish the P2P connections eagerly (outside any graph capture) with one exchange of each kind
+        float* t = s->acquire();
+        if (!t) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        F2D_CUDA(cudaMemsetAsync(t, 0, s->field_bytes, s->stream));
+        const float* one[1] = {t};
+        int rc = s->exchange(one, 1);
+        if (rc == F2D_OK) rc = s->reverse_exchange_add(t);
+        s->release(t);
+        if (rc != F2D_OK) return rc;
+        F2D_CUDA(cudaStreamSynchronize(s->stream));
+        s->exchanges = 0;
+        s->inv_table.clear();
+    }
+    if (s->graph_exec) {  // a graph captured before had no exchanges in it
+        cudaGraphExecDestroy(s->graph_exec);
+        s->graph_exec = nullptr;
+        s->graph_key.valid = false;
+    }
+    return F2D_OK;
+}
+
+F2D_API int f2d_comm_stats(const f2d_solver* s, uint64_t* exchanges) {
+    if (!s || !exchanges) return fail(F2D_ERR_INVALID, "NULL argument");
+    *exchanges = s->exchanges;
+    return F2D_OK;
+}
 
 F2D_API const char* f2d_last_error(void) { return g_err; }
 F2D_API int f2d_abi_version(void) { return F2D_ABI_VERSION; }
@@ -450,7 +729,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
             return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc(%zu) failed: %s", s->field_bytes, cudaGetErrorString(cudaGetLastError())));
         cudaMemsetAsync(s->state[i], 0, s->field_bytes, s->stream);
     }
-    const int ntemps = 9;  // deepest point: velocity chain during project (2+2 diffuse, 2 advect, div, 2 p)
+    const int ntemps = 11;  // deepest point: batched diffuse (2 add_sources outputs + 3x2 ping-pong + p/div views)
     for (int i = 0; i < ntemps; ++i) {
         float* p = nullptr;
         if (cudaMalloc(&p, s->field_bytes) != cudaSuccess)
@@ -479,6 +758,9 @@ F2D_API void f2d_destroy(f2d_solver* s) {
         if (s->state[i]) cudaFree(s->state[i]);
     for (float* p : s->temps) cudaFree(p);
     if (s->oob_flag) cudaFree(s->oob_flag);
+    if (s->rx_up) cudaFree(s->rx_up);
+    if (s->rx_down) cudaFree(s->rx_down);
+    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -612,6 +894,7 @@ F2D_API int f2d_stage_add_sources(f2d_solver* s, int field, float dt) {
     AddSourceBatch ab;
     ab.n = 1;
     ab.f[0] = s->state[field];
+    ab.o[0] = s->state[field];
     ab.s[0] = s->state[field + 3];
     launch_add_sources(s->g, ab, dt, s->stream);
     s->count();
@@ -672,7 +955,7 @@ F2D_API int f2d_stage_advect_velocity(f2d_solver* s, float dt) {
     if (!u0 || !v0) return fail(F2D_ERR_STATE, "scratch pool exhausted");
     F2D_TRY(copy_back(s, u0, u));  // gpu.cu:248-249
     F2D_TRY(copy_back(s, v0, v));
-    launch_advect_velocity(s->g, u0, v0, u, v, s->dt0(dt), s->stream);
+    launch_advect_velocity(s->g, u0, v0, u, v, s->dt0(dt), s->own_begin(), s->own_end(), s->oob_flag, s->stream);
     s->count();
     s->release(u0);
     s->release(v0);

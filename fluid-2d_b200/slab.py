@@ -1,0 +1,84 @@
+"""Row-slab decomposition for the multi-GPU path (one process per GPU, torch.distributed plumbing).
+
+The global N-row grid is cut into `world` contiguous blocks of rows (global edge rows 0 and N-1
+belong to the first / last block).  Rank r holds its block plus `halo` rows of each neighbour; the
+CUDA library exchanges those rows over NCCL (f2d_comm_*, include/f2d.h).  Nothing here computes:
+this module only derives slab geometry, slices host arrays and wires the communicator.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import capi
+from .solver import FluidSolverB200
+
+
+@dataclass(frozen=True)
+class Slab:
+    rank: int
+    world: int
+    global_rows: int
+    halo: int
+    own_begin: int   # global row range owned by this rank: [own_begin, own_end)
+    own_end: int
+    row_offset: int  # global row of local row 0
+    rows: int        # local rows including halos
+
+    @property
+    def local_own(self):
+        """Owned rows in local coordinates."""
+        return self.own_begin - self.row_offset, self.own_end - self.row_offset
+
+
+def partition(global_rows, world, halo, rank):
+    """Slab of `rank`.  Blocks differ by at most one row; every block must be >= 3 halos deep."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(global_rows, world)
+    begin = rank * base + min(rank, rem)
+    end = begin + base + (1 if rank < rem else 0)
+    lo = max(0, begin - halo) if rank > 0 else 0
+    hi = min(global_rows, end + halo) if rank < world - 1 else global_rows
+    if world > 1 and (end - begin) < max(1, halo):
+        raise ValueError("slab of %d rows is thinner than the halo (%d)" % (end - begin, halo))
+    return Slab(rank, world, global_rows, halo if world > 1 else 0, begin, end, lo, hi - lo)
+
+
+def take(slab, a):
+    """Local slab (halo rows included) of a global host array."""
+    return np.ascontiguousarray(a[slab.row_offset:slab.row_offset + slab.rows])
+
+
+def put_owned(slab, dst, local):
+    """Write the owned rows of a local slab back into a global host array."""
+    b, e = slab.local_own
+    dst[slab.own_begin:slab.own_end] = local[b:e]
+
+
+def broadcast_unique_id(dist, rank, device=None):
+    """Rank 0 creates the 128-byte NCCL id (f2d_comm_unique_id); torch.distributed broadcasts it."""
+    import torch
+
+    buf = torch.zeros(128, dtype=torch.uint8, device=device if device is not None else "cpu")
+    if rank == 0:
+        raw = C.create_string_buffer(128)
+        capi.check(capi.load().f2d_comm_unique_id(raw))
+        buf.copy_(torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def make_slab_solver(slab, cols, unique_id, cfl_cells=8, device=0, **solver_kwargs):
+    """FluidSolverB200 for one slab, communicator initialised (collective over all ranks)."""
+    s = FluidSolverB200(slab.rows, cols, global_rows=slab.global_rows, row_offset=slab.row_offset,
+                        halo=slab.halo, device=device, **solver_kwargs)
+    if slab.world > 1:
+        capi.check(capi.load().f2d_comm_init(s._h, unique_id, slab.rank, slab.world, cfl_cells))
+    return s
+
+
+def comm_exchanges(solver):
+    n = C.c_uint64()
+    capi.check(capi.load().f2d_comm_stats(solver._h, C.byref(n)))
+    return int(n.value)

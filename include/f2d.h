@@ -146,6 +146,21 @@ F2D_API int f2d_bench_jacobi(f2d_solver* s, int diffuse_like, uint32_t iters, ui
 /* number of kernel launches (graph kernel nodes included) issued by this solver so far */
 F2D_API int f2d_launch_count(const f2d_solver* s, uint64_t* launches);
 
+/* ---- multi-GPU row slabs (one process per GPU) ------------------------------------------------
+ * New work: the reference is single-GPU.  Each rank holds one slab of rows
+ * (f2d_config.row_offset / global_rows / halo); neighbouring slabs exchange `halo` rows over
+ * NCCL send/recv (NVLink) whenever a stencil stage would otherwise invalidate owned rows: once per
+ * halo/temporal_block relaxation passes, around the advection (radius cfl_cells + 1), and -- in the
+ * reverse direction, with an add -- after the density scatter.  The exchanges run on the solver's
+ * stream and are part of the step's CUDA graph.
+ *   f2d_comm_unique_id : rank 0 creates the 128-byte NCCL id; the host side broadcasts it.
+ *   f2d_comm_init      : collective; rank r must hold the r-th slab from the top.  cfl_cells is
+ *                        the caller's bound on the advection displacement per step (cells);
+ *                        f2d_sync reports F2D_ERR_STATE if a step exceeded it. */
+F2D_API int f2d_comm_unique_id(char* id128);
+F2D_API int f2d_comm_init(f2d_solver* s, const char* id128, int rank, int nranks, int cfl_cells);
+F2D_API int f2d_comm_stats(const f2d_solver* s, uint64_t* exchanges);
+
 /* ---- interop ------------------------------------------------------------------------------- */
 /* device pointer + pitch (in floats) of a state field, for zero-copy views (torch, NCCL halos) */
 F2D_API int f2d_field_ptr(f2d_solver* s, int field, void** device_ptr, size_t* pitch_elems);
