@@ -197,6 +197,7 @@ def run_single_gpu(args, workload):
     jac_gbs = 12.0 * jac_cell_iters / (jac_ms * 1e-3) / 1e9
     dif_ms = solver.bench_jacobi(True, kd, reps)
     dif_gbs = 12.0 * cells * kd * reps / (dif_ms * 1e-3) / 1e9
+    Td = int(cfg.temporal_block_diffuse)
 
     # ---- end to end through the reference interface: solve() on pinned host grids
     pins = pinned_like(fields)
@@ -224,14 +225,14 @@ def run_single_gpu(args, workload):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload["name"], "grid": [n, n], "diffuse_iters": kd, "project_iters": kp,
                    "smooth": True, "dt": DT, "diffusion_rate": DIFFUSION_RATE, "viscosity": VISCOSITY,
-                   "jacobi_mode": int(cfg.jacobi_mode), "temporal_block": T, "divide_mode": int(cfg.divide_mode),
+                   "jacobi_mode": int(cfg.jacobi_mode), "temporal_block": T, "temporal_block_diffuse": int(cfg.temporal_block_diffuse), "divide_mode": int(cfg.divide_mode),
                    "cuda_graph": bool(cfg.use_graph),
                    "l2": "inputs larger than L2 (>= 13 fields x %.0f MiB)" % (cells * 4 / 2**20)},
         "roofline": {"bound": "hbm", "kernel": "k_jacobi_stream (pressure relaxation, %d sweeps per launch)" % T,
                      "achieved": jac_gbs, "peak": peak, "unit": "GB/s", "frac": jac_gbs / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_cell_sweep": 12,
                      "avg_launch_ms": jac_ms / passes, "launches_timed": passes,
-                     "diffuse_kernel": {"achieved": dif_gbs, "frac": dif_gbs / peak},
+                     "diffuse_kernel": {"achieved": dif_gbs, "frac": dif_gbs / peak, "sweeps_per_launch": Td},
                      "step": {"bytes_per_cell_step": bps, "achieved": bps * value / 1e9, "frac": bps * value / 1e9 / peak}},
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": kind,
                          "sample": "1 step of a %dx%d grid, Kd=Kp=%d, fluid_solver_cpu (Gauss-Seidel, 1 thread; %d host cores present)"

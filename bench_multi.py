@@ -109,7 +109,7 @@ def run_multi_gpu(args, workload):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload["name"], "grid": [n, n], "diffuse_iters": kd, "project_iters": kp,
                        "parallelism": "row slabs x%d, halo %d rows, NCCL send/recv in the step graph" % (world, halo),
-                       "temporal_block": int(cfg.temporal_block), "jacobi_mode": int(cfg.jacobi_mode),
+                       "temporal_block": int(cfg.temporal_block), "temporal_block_diffuse": int(cfg.temporal_block_diffuse), "jacobi_mode": int(cfg.jacobi_mode),
                        "divide_mode": int(cfg.divide_mode), "cfl_cells": cfl,
                        "l2": "inputs larger than L2 (slab fields of %.0f MiB)" % (sl.rows * n * 4 / 2**20)},
             "roofline": {"bound": "hbm", "kernel": "whole step, algorithmic bytes (SURVEY 8d)", "achieved": bps * value / 1e9,

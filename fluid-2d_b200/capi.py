@@ -43,7 +43,7 @@ class SolverConfig(C.Structure):
         ("global_rows", C.c_uint32),
         ("row_offset", C.c_uint32),
         ("halo", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("temporal_block_diffuse", C.c_uint32),
         ("stream", C.c_void_p),
     ]
 

@@ -32,6 +32,8 @@
 //   * The row loop is unrolled by RS (a multiple of 3) so that all window/ring register indices
 //     are compile-time constants; blocks of RS rows in which every level is strictly inside the
 //     chunk take a FAST path without any range or edge-row checks.
+#include <algorithm>
+
 #include "f2d_kernels.cuh"
 
 namespace f2d {
@@ -40,7 +42,7 @@ namespace {
 
 constexpr int kLanes = 32;
 constexpr int kStripFloats = 128;  // one float4 per lane
-constexpr int kPFD = 4;            // async prefetch distance in rows
+constexpr int kPFD = 6;            // async prefetch distance in rows
 constexpr int kRingP = 8;          // ring slots for the iterate rows (power of two, >= PFD + 2)
 
 __host__ __device__ constexpr int halo_of(int T) { return T <= 4 ? 4 : ((T + 3) / 4) * 4; }
@@ -53,8 +55,15 @@ __host__ __device__ constexpr int ring_r_of(int T, bool rhs_regs) {
     return rhs_regs ? kRingP : ((kPFD + T + 2) <= 8 ? 8 : 16);
 }
 
+// Work decomposition.  Warps fall into two classes with different cost per row: class 0 = interior
+// strips, class 1 = the strips that hold a left/right domain edge column (extra edge fix per level).
+// Each class has its own chunk height so that all warps of a launch finish together; the first and
+// last chunk of a class are `edge_trim` rows shorter to pay for their checked edge-row steps.
 struct StreamPlan {
-    int strips, chunks, chunk_rows, bw, edge_trim;
+    int strips, bw;
+    int warps_int;      // warps of class 0: (strips - n_edge_strips) * chunks[0]
+    int n_edge_strips;  // 0, 1 or 2
+    int chunks[2], chunk_rows[2], edge_trim[2];
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
@@ -124,7 +133,7 @@ struct Ctx {
 // row (edge rule, corner carry) take the checked path (FAST == false).
 template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS, bool FAST, int RS, int RINGR, int NRH>
 __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, float4 (&W)[T][3], float4 (&RH)[NRH],
-                                          float4& out_prev) {
+                                          float4& out_prev, float (&wl)[T], float (&er)[T]) {
 #pragma unroll
     for (int k = 0; k < RS; ++k) {
         const int rr = rb + k;
@@ -151,18 +160,8 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
             if (RHS_REGS) RH[mrs(k, RS)] = cx.ring_r[(r & (RINGR - 1)) * kLanes];
         }
 
-        // 3. west/east neighbours of the centre rows of ALL levels: those rows were produced in the
-        //    previous step, so the 2T shuffles are issued up front and their latency overlaps the
-        //    arithmetic of the lower levels
-        float wl[T], er[T];
-#pragma unroll
-        for (int s = 0; s < T; ++s) {
-            const float4 b = W[s][m3(k - s - 1)];
-            wl[s] = __shfl_up_sync(0xffffffffu, b.w, 1);
-            er[s] = __shfl_down_sync(0xffffffffu, b.x, 1);
-        }
-
-        // 4. level s+1 produces row q = r - s - 1 from level s rows q-1, q, q+1.
+        // 3. level s+1 produces row q = r - s - 1 from level s rows q-1, q, q+1; the west/east
+        //    neighbours wl[s], er[s] of the centre row were shuffled at the end of the previous step.
         //    active levels: rs+1 <= q <= re-1  <=>  s_lo <= s <= s_hi
         const int s_lo = r - cx.re, s_hi = r - cx.rs - 2;
         const int s_top = cx.top_dom ? r - 2 : -1;           // level whose q == 1 (global top edge above it)
@@ -181,11 +180,11 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
                 else
                     rhs = cx.ring_r[(q & (RINGR - 1)) * kLanes];
                 float4 nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
-                if (cx.edge_warp) {  // warp-uniform: this strip touches the left/right domain edge
-                    // interior rows: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32)
-                    if (cx.has_left) nw.x = apply_sign(nw.y, cx.neg_c);
-                    if (cx.has_right) nw.w = apply_sign(nw.z, cx.neg_c);
-                }
+                // interior rows: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32).  Written as
+                // two predicated selects (no branch) so that a whole row step stays one basic block and
+                // the scheduler can overlap the tail of one level with the head of the next.
+                nw.x = cx.has_left ? apply_sign(nw.y, cx.neg_c) : nw.x;
+                nw.w = cx.has_right ? apply_sign(nw.z, cx.neg_c) : nw.w;
                 if (s + 1 < T) {
                     W[sn][sm] = nw;
                 } else {
@@ -208,11 +207,20 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
                     st_global_f4(cx.next + (size_t)q * cx.pitch, e);
             }
         }
+        // 4. the centre row of level s in the NEXT step is row r - s (slot m3(k - s)); it is final now,
+        //    so its west/east shuffles are issued here and complete while the next row is fetched
+#pragma unroll
+        for (int s = 0; s < T; ++s) {
+            const float4 b = W[s][m3(k - s)];
+            wl[s] = __shfl_up_sync(0xffffffffu, b.w, 1);
+            er[s] = __shfl_down_sync(0xffffffffu, b.x, 1);
+        }
     }
 }
 
-template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS>
-__global__ void __launch_bounds__(256) k_jacobi_stream(Geom g, RelaxBatch batch, StreamPlan plan) {
+// MINB = resident CTAs (of 128 threads) per SM the register allocator must allow
+template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch batch, StreamPlan plan) {
     constexpr int HALO = halo_of(T);
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;  // unroll factor of the row loop
     constexpr int RINGR = ring_r_of(T, RHS_REGS);
@@ -223,9 +231,21 @@ __global__ void __launch_bounds__(256) k_jacobi_stream(Geom g, RelaxBatch batch,
     const int warp_in_cta = threadIdx.x >> 5;
     const int warps_per_cta = blockDim.x >> 5;
     const int gw = blockIdx.x * warps_per_cta + warp_in_cta;
-    const int strip = gw % plan.strips;
-    const int chunk = gw / plan.strips;
-    if (chunk >= plan.chunks) return;  // whole warp leaves; there is no block-wide barrier
+    int cls, strip, chunk;
+    if (gw < plan.warps_int) {  // interior strips: 1 .. strips-2 (or 0 .. when there is no edge strip)
+        cls = 0;
+        const int ns = plan.strips - plan.n_edge_strips;
+        strip = (plan.n_edge_strips ? 1 : 0) + gw % ns;
+        chunk = gw / ns;
+    } else {  // the strips holding column 0 / column cols-1
+        cls = 1;
+        const int e = gw - plan.warps_int;
+        if (plan.n_edge_strips == 0) return;
+        strip = (e % plan.n_edge_strips == 0) ? 0 : plan.strips - 1;
+        chunk = e / plan.n_edge_strips;
+    }
+    const int n_chunks = plan.chunks[cls], chunk_rows = plan.chunk_rows[cls], edge_trim = plan.edge_trim[cls];
+    if (chunk >= n_chunks) return;  // whole warp leaves; there is no block-wide barrier
 
     const RelaxField& fld = batch.f[blockIdx.y];
     Ctx cx;
@@ -251,8 +271,8 @@ __global__ void __launch_bounds__(256) k_jacobi_stream(Geom g, RelaxBatch batch,
 
     // ---- rows of this warp (local row indices)
     // the first / last chunk are `edge_trim` rows shorter: their edge-rule steps cost more
-    cx.y0 = (chunk == 0) ? 0 : chunk * plan.chunk_rows - plan.edge_trim;
-    cx.y1 = (chunk == plan.chunks - 1) ? g.rows : (chunk + 1) * plan.chunk_rows - plan.edge_trim;
+    cx.y0 = (chunk == 0) ? 0 : chunk * chunk_rows - edge_trim;
+    cx.y1 = (chunk == n_chunks - 1) ? g.rows : (chunk + 1) * chunk_rows - edge_trim;
     // T warm-up rows above the first owned row; a chunk that owns only the global bottom edge row
     // must warm up for row rows-2, which the edge rule copies from
     cx.rs = max(0, min(cx.y0, g.rows - 2) - T);
@@ -273,10 +293,13 @@ __global__ void __launch_bounds__(256) k_jacobi_stream(Geom g, RelaxBatch batch,
     float4 W[T][3];
     float4 RH[NRH];
     float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wl[T], er[T];
 #pragma unroll
-    for (int s = 0; s < T; ++s)
+    for (int s = 0; s < T; ++s) {
+        wl[s] = er[s] = 0.f;
 #pragma unroll
         for (int m = 0; m < 3; ++m) W[s][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int m = 0; m < NRH; ++m) RH[m] = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -296,21 +319,50 @@ __global__ void __launch_bounds__(256) k_jacobi_stream(Geom g, RelaxBatch batch,
         const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
         const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
         if (!edge_block)
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev);
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er);
         else
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev);
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er);
     }
     cp_async_wait<0>();
 }
 
-// One wave, every resident warp slot busy: the chunk height is chosen so that the number of CTAs is
-// the largest value <= (CTAs resident per SM) x (SM count); all warps then run concurrently and finish
-// together.  At least 4T output rows per chunk bound the warm-up redundancy on small grids.
-template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS>
+// Host-side planner.  One wave, every resident warp slot busy, all warps finishing together:
+//   cost(warp) = (rows of its chunk + 2T warm-up rows) * c_class  [+ checked edge-row steps]
+// with c_class the instruction count of one row step (interior strip : edge strip ~ 1 : kEdgeStripCost,
+// read off the SASS).  The largest chunk heights whose warp count fits the resident slots are found
+// by bisection on the common cost.  First/last chunks are trimmed by the cost of their checked steps.
+constexpr double kEdgeStripCost = 1.0;   // edge strips cost the same since the edge-column fix is branch-free
+constexpr double kCheckedStepCost = 3.4; // checked (global edge row) step relative to a fast step
+
+struct ClassPlan {
+    int chunks, chunk_rows, trim;
+};
+
+inline ClassPlan plan_class(int rows, int T, int RS, double cost_budget, double c_class, bool both_edges) {
+    ClassPlan cp;
+    int ch = (int)(cost_budget / c_class) - 2 * T;  // rows per chunk at this budget
+    ch = std::max(ch, 4 * T);
+    ch = std::min(ch, rows);
+    int trim = both_edges ? (int)((T + RS / 2) * (kCheckedStepCost - 1.0)) : 0;
+    if (ch < 2 * trim + 2 || ch >= rows) trim = 0;
+    int chunks = (rows + 2 * trim + ch - 1) / ch;
+    while (chunks > 1 && (chunks - 1) * ch - trim >= rows) --chunks;
+    if (chunks < 3) {
+        trim = 0;
+        chunks = (rows + ch - 1) / ch;
+    }
+    cp.chunks = chunks;
+    cp.chunk_rows = ch;
+    cp.trim = trim;
+    return cp;
+}
+
+template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS, int MINB>
 void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, int sm_count, cudaStream_t st) {
-    auto kern = k_jacobi_stream<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS>;
+    auto kern = k_jacobi_stream<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, MINB>;
+    constexpr int RS = RHS_REGS ? rs_of(T) : 3;
     int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
-    wpc = min(wpc, 8);
+    wpc = std::min(wpc, 4);  // __launch_bounds__(128, ...)
     const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS)) * kLanes * sizeof(float4);
     static int occ_cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (occ_cache[wpc] == 0) {
@@ -322,45 +374,54 @@ void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, in
     StreamPlan plan;
     plan.bw = kStripFloats - 2 * halo_of(T);
     plan.strips = (g.cols + plan.bw - 1) / plan.bw;
-    int chunk_rows = tune.chunk_rows;
-    int trim = (g.grow0 == 0 && g.grow0 + g.rows == g.grows) ? 4 * T + 2 : 0;  // both global edges in this field
-    if (chunk_rows <= 0) {
-        const long warp_slots = (long)occ_cache[wpc] * sm_count * wpc;
-        long chunks = warp_slots / ((long)plan.strips * b.n);
-        if (chunks < 1) chunks = 1;
-        if (chunks < 3) trim = 0;
-        chunk_rows = (int)((g.rows + 2 * trim + chunks - 1) / chunks);
-        if (chunk_rows < 4 * T) {
-            chunk_rows = 4 * T;
-            trim = 0;
-        }
+    plan.n_edge_strips = std::min(plan.strips, 2);
+    const int n_int = plan.strips - plan.n_edge_strips;
+    const bool both_edges = (g.grow0 == 0 && g.grow0 + g.rows == g.grows);
+    const long slots = (long)occ_cache[wpc] * sm_count * wpc / b.n;  // warps available per field
+    ClassPlan ci = {0, 0, 0}, ce = {0, 0, 0};
+    if (tune.chunk_rows > 0) {  // manual override: same height for both classes, no trimming
+        ci.chunk_rows = ce.chunk_rows = std::min(tune.chunk_rows, g.rows);
+        ci.chunks = ce.chunks = (g.rows + ci.chunk_rows - 1) / ci.chunk_rows;
     } else {
-        trim = 0;
+        // smallest common cost whose warp count fits the resident slots
+        double lo = 4.0 * T, hi = (double)(g.rows + 2 * T) * kEdgeStripCost + 1.0;
+        for (int it = 0; it < 40; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            const ClassPlan a = plan_class(g.rows, T, RS, mid, 1.0, both_edges);
+            const ClassPlan e = plan_class(g.rows, T, RS, mid, kEdgeStripCost, both_edges);
+            const long warps = (long)n_int * a.chunks + (long)plan.n_edge_strips * e.chunks;
+            if (warps <= slots)
+                hi = mid;
+            else
+                lo = mid;
+        }
+        ci = plan_class(g.rows, T, RS, hi, 1.0, both_edges);
+        ce = plan_class(g.rows, T, RS, hi, kEdgeStripCost, both_edges);
     }
-    chunk_rows = min(chunk_rows, g.rows);
-    if (chunk_rows < 2 * trim + 2) trim = 0;
-    plan.chunk_rows = chunk_rows;
-    plan.edge_trim = trim;
-    plan.chunks = (g.rows + 2 * trim + chunk_rows - 1) / chunk_rows;
-    while (plan.chunks > 1 && (plan.chunks - 1) * chunk_rows - trim >= g.rows) --plan.chunks;
-    if (plan.chunks == 1) plan.edge_trim = 0;
-    const int total_warps = plan.strips * plan.chunks;
-    dim3 grid((total_warps + wpc - 1) / wpc, b.n);
+    plan.chunks[0] = ci.chunks;
+    plan.chunk_rows[0] = ci.chunk_rows;
+    plan.edge_trim[0] = ci.trim;
+    plan.chunks[1] = ce.chunks;
+    plan.chunk_rows[1] = ce.chunk_rows;
+    plan.edge_trim[1] = ce.trim;
+    plan.warps_int = n_int * ci.chunks;
+    const long total_warps = (long)plan.warps_int + (long)plan.n_edge_strips * ce.chunks;
+    dim3 grid((unsigned)((total_warps + wpc - 1) / wpc), b.n);
     kern<<<grid, wpc * 32, smem, st>>>(g, b, plan);
 }
 
-template <int T, bool RHS_REGS>
+template <int T, bool RHS_REGS, int MINB>
 void launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, const StreamTuning& tune, int sm_count,
               cudaStream_t st) {
     if (!diffuse) {
         if (b.f[0].prev == nullptr)
-            launch_one<T, false, F2D_DIV_F64, true, RHS_REGS>(g, b, tune, sm_count, st);
+            launch_one<T, false, F2D_DIV_F64, true, RHS_REGS, MINB>(g, b, tune, sm_count, st);
         else
-            launch_one<T, false, F2D_DIV_F64, false, RHS_REGS>(g, b, tune, sm_count, st);
+            launch_one<T, false, F2D_DIV_F64, false, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     } else if (divmode == F2D_DIV_F64) {
-        launch_one<T, true, F2D_DIV_F64, false, RHS_REGS>(g, b, tune, sm_count, st);
+        launch_one<T, true, F2D_DIV_F64, false, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     } else {
-        launch_one<T, true, F2D_DIV_F32_CORR, false, RHS_REGS>(g, b, tune, sm_count, st);
+        launch_one<T, true, F2D_DIV_F32_CORR, false, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     }
 }
 
@@ -375,13 +436,27 @@ void launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int 
                           const StreamTuning& tune, int sm_count, cudaStream_t st) {
     (void)sweeps;  // == T: the step driver decomposes K into passes of 8/4/2/1 sweeps
     // T = 8 keeps the right-hand side in the smem ring (unroll 3): with a register ring the unrolled
-    // row loop (9 x 8 levels) outgrows the instruction cache
+    // row loop (9 x 8 levels) outgrows the instruction cache.  min_blocks picks the register budget
+    // (resident 128-thread CTAs per SM): T = 8 -> 3 (168 regs) or 2, T = 4 -> 4 (128 regs) or 5.
     const bool rr = (tune.rhs_in_smem == 0) && T < 8;
+    const int mb = tune.min_blocks;
     switch (T) {
-        case 1: rr ? launch_T<1, true>(g, b, diffuse, divmode, tune, sm_count, st) : launch_T<1, false>(g, b, diffuse, divmode, tune, sm_count, st); break;
-        case 2: rr ? launch_T<2, true>(g, b, diffuse, divmode, tune, sm_count, st) : launch_T<2, false>(g, b, diffuse, divmode, tune, sm_count, st); break;
-        case 4: rr ? launch_T<4, true>(g, b, diffuse, divmode, tune, sm_count, st) : launch_T<4, false>(g, b, diffuse, divmode, tune, sm_count, st); break;
-        default: launch_T<8, false>(g, b, diffuse, divmode, tune, sm_count, st); break;
+        case 1: launch_T<1, true, 6>(g, b, diffuse, divmode, tune, sm_count, st); break;
+        case 2: launch_T<2, true, 6>(g, b, diffuse, divmode, tune, sm_count, st); break;
+        case 4:
+            if (rr)
+                launch_T<4, true, 4>(g, b, diffuse, divmode, tune, sm_count, st);
+            else if (mb == 5)
+                launch_T<4, false, 5>(g, b, diffuse, divmode, tune, sm_count, st);
+            else
+                launch_T<4, false, 4>(g, b, diffuse, divmode, tune, sm_count, st);
+            break;
+        default:
+            if (mb == 2)
+                launch_T<8, false, 2>(g, b, diffuse, divmode, tune, sm_count, st);
+            else
+                launch_T<8, false, 3>(g, b, diffuse, divmode, tune, sm_count, st);
+            break;
     }
 }
 

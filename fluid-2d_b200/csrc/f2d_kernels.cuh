@@ -50,6 +50,7 @@ struct StreamTuning {
     int chunk_rows;     // output rows per warp (0 = auto)
     int warps_per_cta;  // 0 = auto
     int rhs_in_smem;    // 0 = rhs rows ride in a register ring (default), 1 = re-read from the smem ring
+    int min_blocks;     // 0 = default register budget; see launch_jacobi_stream
 };
 // `sweeps` (1..T) Jacobi sweeps in one pass over the field(s); returns false if (T, geometry)
 // is not supported by the streaming kernel.

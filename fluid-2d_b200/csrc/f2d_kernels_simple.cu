@@ -34,8 +34,66 @@ __global__ void __launch_bounds__(kBx* kBy) k_add_sources(Geom g, AddSourceBatch
         out[o] = f[o];
 }
 
+// ---- float4 row kernels (cols % 4 == 0): one thread = four consecutive cells of one row ----------
+// Columns 0/1 and cols-2/cols-1 then share a float4, so the fused boundary pass needs no second
+// evaluation: the edge column takes +/- its neighbour component, an edge ROW is produced by
+// evaluating the adjacent interior row, corners pass the input through.
+namespace {
+constexpr int kVx = 64, kVy = 4;
+inline dim3 grid_v4(const Geom& g, int z = 1) { return dim3((g.cols / 4 + kVx - 1) / kVx, (g.rows + kVy - 1) / kVy, z); }
+
+struct RowSrc {
+    int si;        // row whose update is evaluated (== i for interior rows)
+    bool keep;     // pass the input row through (slab-local edge row)
+    bool edge_row; // i is a global top/bottom row
+};
+__device__ __forceinline__ RowSrc classify_row(const Geom& g, int i) {
+    RowSrc r;
+    const int gi = g.grow0 + i;
+    const bool top = (gi == 0), bottom = (gi == g.grows - 1);
+    r.edge_row = top || bottom;
+    r.si = top ? i + 1 : (bottom ? i - 1 : i);
+    r.keep = ((i == 0 && !top) || (i == g.rows - 1 && !bottom));
+    if ((r.si == 0 && g.grow0 != 0) || (r.si == g.rows - 1 && g.grow0 + g.rows != g.grows)) r.keep = true;
+    return r;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 neg4(const float4& v, bool n) {
+    return n ? make_float4(-v.x, -v.y, -v.z, -v.w) : v;
+}
+#define F2D_ROW_J4()                                        \
+    const int jg = blockIdx.x * kVx + threadIdx.x;          \
+    const int i = blockIdx.y * kVy + threadIdx.y;           \
+    const int j = 4 * jg;                                   \
+    if (i >= g.rows || j >= g.cols) return;
+}  // namespace
+
+__global__ void __launch_bounds__(kVx* kVy) k_add_sources_v4(Geom g, AddSourceBatch b, float dt) {
+    F2D_ROW_J4();
+    const int gi = g.grow0 + i;
+    const size_t o = (size_t)i * g.pitch + j;
+    const float* __restrict__ f = b.f[blockIdx.z];
+    float* out = b.o[blockIdx.z];
+    const float4 fv = ld4(f + o);
+    if (gi < 1 || gi > g.grows - 2) {
+        if (out != f) st4(out + o, fv);
+        return;
+    }
+    const float4 sv = ld4(b.s[blockIdx.z] + o);
+    float4 r;
+    r.x = (j == 0) ? fv.x : __fmaf_rn(dt, sv.x, fv.x);
+    r.y = __fmaf_rn(dt, sv.y, fv.y);
+    r.z = __fmaf_rn(dt, sv.z, fv.z);
+    r.w = (j + 3 == g.cols - 1) ? fv.w : __fmaf_rn(dt, sv.w, fv.w);
+    st4(out + o, r);
+}
+
 void launch_add_sources(const Geom& g, const AddSourceBatch& b, float dt, cudaStream_t st) {
-    k_add_sources<<<grid2d(g, b.n), dim3(kBx, kBy), 0, st>>>(g, b, dt);
+    if (g.cols % 4 == 0)
+        k_add_sources_v4<<<grid_v4(g, b.n), dim3(kVx, kVy), 0, st>>>(g, b, dt);
+    else
+        k_add_sources<<<grid2d(g, b.n), dim3(kBx, kBy), 0, st>>>(g, b, dt);
 }
 
 // --------------------------------------------------------------------------- naive Jacobi
@@ -97,8 +155,36 @@ __global__ void __launch_bounds__(kBx* kBy) k_divergence(Geom g, const float* __
     dv[o] = divergence_update(u[so + 1], u[so - 1], v[so + g.pitch], v[so - g.pitch], mhalf_h);
 }
 
+__global__ void __launch_bounds__(kVx* kVy) k_divergence_v4(Geom g, const float* __restrict__ u,
+                                                           const float* __restrict__ v, float* __restrict__ dv,
+                                                           float mhalf_h) {
+    F2D_ROW_J4();
+    const RowSrc rs = classify_row(g, i);
+    const size_t o = (size_t)i * g.pitch + j;
+    if (rs.keep) {
+        st4(dv + o, make_float4(0.f, 0.f, 0.f, 0.f));
+        return;
+    }
+    const size_t so = (size_t)rs.si * g.pitch + j;
+    const float4 uc = ld4(u + so), vs = ld4(v + so + g.pitch), vn = ld4(v + so - g.pitch);
+    const float ul = (j > 0) ? __ldg(u + so - 1) : 0.f;
+    const float ur = (j + 4 < g.cols) ? __ldg(u + so + 4) : 0.f;
+    float4 r;
+    r.x = divergence_update(uc.y, ul, vs.x, vn.x, mhalf_h);
+    r.y = divergence_update(uc.z, uc.x, vs.y, vn.y, mhalf_h);
+    r.z = divergence_update(uc.w, uc.y, vs.z, vn.z, mhalf_h);
+    r.w = divergence_update(ur, uc.z, vs.w, vn.w, mhalf_h);
+    // set_boundary_continuous: edge columns copy their neighbour, corners stay 0 (the memset of gpu.cu:363)
+    if (j == 0) r.x = rs.edge_row ? 0.f : r.y;
+    if (j + 3 == g.cols - 1) r.w = rs.edge_row ? 0.f : r.z;
+    st4(dv + o, r);
+}
+
 void launch_divergence(const Geom& g, const float* u, const float* v, float* dv, float h, cudaStream_t st) {
-    k_divergence<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u, v, dv, -0.5f * h);
+    if (g.cols % 4 == 0)
+        k_divergence_v4<<<grid_v4(g), dim3(kVx, kVy), 0, st>>>(g, u, v, dv, -0.5f * h);
+    else
+        k_divergence<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u, v, dv, -0.5f * h);
 }
 
 // ------------------------------------------------------------------------------- gradient
@@ -125,9 +211,54 @@ __global__ void __launch_bounds__(kBx* kBy) k_gradient(Geom g, const float* __re
     v_out[o] = apply_sign(vn, cv.negate);
 }
 
+__global__ void __launch_bounds__(kVx* kVy) k_gradient_v4(Geom g, const float* __restrict__ p,
+                                                         const float* __restrict__ u_in,
+                                                         const float* __restrict__ v_in, float* __restrict__ u_out,
+                                                         float* __restrict__ v_out, float h) {
+    F2D_ROW_J4();
+    const RowSrc rs = classify_row(g, i);
+    const size_t o = (size_t)i * g.pitch + j;
+    const float4 u_here = ld4(u_in + o), v_here = ld4(v_in + o);
+    if (rs.keep) {
+        st4(u_out + o, u_here);
+        st4(v_out + o, v_here);
+        return;
+    }
+    const size_t so = (size_t)rs.si * g.pitch + j;
+    const float4 pc = ld4(p + so), ps = ld4(p + so + g.pitch), pn = ld4(p + so - g.pitch);
+    const float pl = (j > 0) ? __ldg(p + so - 1) : 0.f;
+    const float pr = (j + 4 < g.cols) ? __ldg(p + so + 4) : 0.f;
+    const float4 us = rs.edge_row ? ld4(u_in + so) : u_here, vsrc = rs.edge_row ? ld4(v_in + so) : v_here;
+    float4 un, vn;
+    un.x = gradient_update(us.x, pc.y, pl, h);
+    un.y = gradient_update(us.y, pc.z, pc.x, h);
+    un.z = gradient_update(us.z, pc.w, pc.y, h);
+    un.w = gradient_update(us.w, pr, pc.z, h);
+    vn.x = gradient_update(vsrc.x, ps.x, pn.x, h);
+    vn.y = gradient_update(vsrc.y, ps.y, pn.y, h);
+    vn.z = gradient_update(vsrc.z, ps.z, pn.z, h);
+    vn.w = gradient_update(vsrc.w, ps.w, pn.w, h);
+    // edge rows: u copies (opposite_horizontal), v negates (opposite_vertical) the adjacent interior row
+    if (rs.edge_row) vn = neg4(vn, true);
+    // edge columns of interior rows: u negates, v copies its neighbour; corners keep the input
+    if (j == 0) {
+        un.x = rs.edge_row ? u_here.x : -un.y;
+        vn.x = rs.edge_row ? v_here.x : vn.y;
+    }
+    if (j + 3 == g.cols - 1) {
+        un.w = rs.edge_row ? u_here.w : -un.z;
+        vn.w = rs.edge_row ? v_here.w : vn.z;
+    }
+    st4(u_out + o, un);
+    st4(v_out + o, vn);
+}
+
 void launch_gradient(const Geom& g, const float* p, const float* u_in, const float* v_in, float* u_out,
                      float* v_out, float h, cudaStream_t st) {
-    k_gradient<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, p, u_in, v_in, u_out, v_out, h);
+    if (g.cols % 4 == 0)
+        k_gradient_v4<<<grid_v4(g), dim3(kVx, kVy), 0, st>>>(g, p, u_in, v_in, u_out, v_out, h);
+    else
+        k_gradient<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, p, u_in, v_in, u_out, v_out, h);
 }
 
 // ------------------------------------------------------------------------ advect (gather)

@@ -84,9 +84,16 @@ struct f2d_solver {
     GraphKey graph_key = {0.f, 0.f, 0.f, false};
     uint64_t graph_kernels = 0;  // kernel launches inside one replay of the graph
     uint64_t launches = 0;       // kernel launches issued so far (graph nodes included)
-    StreamTuning tune = {0, 0, 0};
+    StreamTuning tune = {0, 0, 0, 0};
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // solve(): the density field is final long before the velocity projections finish; it is copied
+    // back on a second stream as soon as ev_density fires
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_density = nullptr, ev_copy = nullptr;
+    bool capturing = false;
+    bool host_register = true;
+    std::vector<void*> registered;  // host ranges this solver page-locked (cudaHostRegister)
 
     // ---- scratch pool -------------------------------------------------------------------
     float* acquire() {
@@ -219,7 +226,7 @@ struct f2d_solver {
         while (left > 0) {
             uint32_t T = 1;
             if (stream_mode) {
-                T = cfg.temporal_block;
+                T = diffuse ? cfg.temporal_block_diffuse : cfg.temporal_block;
                 while (T > left) T >>= 1;
             }
             if (multi()) {
@@ -355,6 +362,11 @@ struct f2d_solver {
             count();
             set_inv(d, 1);
             release(sc);
+            // density is final: let solve() start its download while the projections run
+            if (capturing)
+                F2D_CUDA(cudaEventRecordWithFlags(ev_density, stream, cudaEventRecordExternal));
+            else
+                F2D_CUDA(cudaEventRecord(ev_density, stream));
         }
         // ---- velocity: project, self-advect, project (gpu.cu:247-252)
         {
@@ -406,7 +418,9 @@ struct f2d_solver {
         cudaGraph_t graph = nullptr;
         // relaxed mode: NCCL (multi-GPU) may issue its own runtime calls while we capture
         F2D_CUDA(cudaStreamBeginCapture(stream, multi() ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
+        capturing = true;
         int rc = enqueue_step(diffusion_rate, viscosity, dt);
+        capturing = false;
         cudaError_t ce = cudaStreamEndCapture(stream, &graph);
         if (rc != F2D_OK) {
             if (graph) cudaGraphDestroy(graph);
@@ -436,6 +450,29 @@ struct f2d_solver {
             for (uint32_t s = 0; s < nsteps; ++s) F2D_TRY(enqueue_step(diffusion_rate, viscosity, dt));
         }
         return F2D_OK;
+    }
+
+    // Page-lock a caller's host grid once (grid<float> storage is pageable; the reference's copy()
+    // helpers pay the staged-copy price on every call, src/utilities.hpp:57-67).  Best effort.
+    void pin_host(const void* p, size_t bytes) {
+        if (!host_register || !p || bytes < (1u << 20)) return;  // small grids: the staged copy is cheap
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        if (at.type != cudaMemoryTypeUnregistered) return;
+        if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess)
+            registered.push_back(const_cast<void*>(p));
+        else
+            cudaGetLastError();
+    }
+
+    int d2h_on(float* dst, const float* src, cudaStream_t st) {
+        return cudaMemcpy2DAsync(dst, (size_t)g.cols * sizeof(float), src, (size_t)g.pitch * sizeof(float),
+                                 (size_t)g.cols * sizeof(float), (size_t)g.rows, cudaMemcpyDeviceToHost, st) == cudaSuccess
+                   ? F2D_OK
+                   : fail(F2D_ERR_CUDA, "cudaMemcpy2DAsync(D2H) failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
 
     int h2d(float* dst, const float* src) {
@@ -699,19 +736,25 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
 
+    // sweeps fused per pass: 8 is fastest for both relaxations at 4096^2 and 16384^2
+    // (profiles/tune_r01_run5_*.jsonl); the two can be set independently
+    if (s->cfg.temporal_block_diffuse == 0)
+        s->cfg.temporal_block_diffuse =
+            s->cfg.temporal_block ? s->cfg.temporal_block : (uint32_t)env_int("F2D_TEMPORAL_BLOCK_DIFFUSE", env_int("F2D_TEMPORAL_BLOCK", 8));
     if (s->cfg.temporal_block == 0) s->cfg.temporal_block = (uint32_t)env_int("F2D_TEMPORAL_BLOCK", 8);
     if (s->cfg.jacobi_mode == F2D_JACOBI_STREAM) {
-        if (!stream_supported(s->g, (int)s->cfg.temporal_block)) {
+        if (!stream_supported(s->g, (int)s->cfg.temporal_block) || !stream_supported(s->g, (int)s->cfg.temporal_block_diffuse)) {
             delete s;
             return fail(F2D_ERR_INVALID,
                         "F2D_JACOBI_STREAM needs cols %% 4 == 0 and temporal_block in {1,2,4,8}; use F2D_JACOBI_NAIVE");
         }
     } else {
-        s->cfg.temporal_block = 1;
+        s->cfg.temporal_block = s->cfg.temporal_block_diffuse = 1;
     }
     s->tune.chunk_rows = env_int("F2D_STREAM_CHUNK_ROWS", 0);
     s->tune.warps_per_cta = env_int("F2D_STREAM_WARPS_PER_CTA", 0);
     s->tune.rhs_in_smem = env_int("F2D_STREAM_RHS_SMEM", 0);
+    s->tune.min_blocks = env_int("F2D_STREAM_MIN_BLOCKS", 0);
 
     auto cleanup = [&](int rc) {
         f2d_destroy(s);
@@ -741,6 +784,11 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     if (cudaMalloc(&s->oob_flag, sizeof(int)) != cudaSuccess)
         return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
     cudaMemsetAsync(s->oob_flag, 0, sizeof(int), s->stream);
+    s->host_register = env_int("F2D_HOST_REGISTER", 1) != 0;
+    if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_density, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming) != cudaSuccess)
+        return cleanup(fail(F2D_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
         return cleanup(fail(F2D_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaStreamSynchronize(s->stream) != cudaSuccess)
@@ -763,6 +811,14 @@ F2D_API void f2d_destroy(f2d_solver* s) {
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->copy_stream) {
+        cudaStreamSynchronize(s->copy_stream);
+        cudaStreamDestroy(s->copy_stream);
+    }
+    if (s->ev_density) cudaEventDestroy(s->ev_density);
+    if (s->ev_copy) cudaEventDestroy(s->ev_copy);
+    for (void* p : s->registered)
+        if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -858,17 +914,26 @@ F2D_API int f2d_solve_host(f2d_solver* s, float* density, const float* density_s
                    const float* u_source, const float* v_source, float viscosity, float dt) {
     F2D_NEED(s);
     if (!density || !density_source || !u || !v || !u_source || !v_source) return fail(F2D_ERR_INVALID, "NULL grid pointer");
+    const size_t host_bytes = (size_t)s->g.rows * s->g.cols * sizeof(float);
+    const void* hosts[6] = {density, u, v, density_source, u_source, v_source};
+    for (const void* h : hosts) s->pin_host(h, host_bytes);
     // upload (gpu.cu:232-234 and the source uploads of :281) -> one step -> download (:255-257)
     F2D_TRY(s->h2d(s->state[F2D_FIELD_DENSITY], density));
+    F2D_TRY(s->h2d(s->state[F2D_FIELD_DENSITY_SOURCE], density_source));
     F2D_TRY(s->h2d(s->state[F2D_FIELD_U], u));
     F2D_TRY(s->h2d(s->state[F2D_FIELD_V], v));
-    F2D_TRY(s->h2d(s->state[F2D_FIELD_DENSITY_SOURCE], density_source));
     F2D_TRY(s->h2d(s->state[F2D_FIELD_U_SOURCE], u_source));
     F2D_TRY(s->h2d(s->state[F2D_FIELD_V_SOURCE], v_source));
     F2D_TRY(s->step(diffusion_rate, viscosity, dt, 1));
-    F2D_TRY(s->d2h(density, s->state[F2D_FIELD_DENSITY]));
+    // density is final once ev_density fires (after the scatter + smooth): download it on the copy stream
+    // while the two projections and the advection are still running
+    F2D_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_density, 0));
+    F2D_TRY(s->d2h_on(density, s->state[F2D_FIELD_DENSITY], s->copy_stream));
+    F2D_CUDA(cudaEventRecord(s->ev_copy, s->copy_stream));
     F2D_TRY(s->d2h(u, s->state[F2D_FIELD_U]));
     F2D_TRY(s->d2h(v, s->state[F2D_FIELD_V]));
+    F2D_CUDA(cudaStreamWaitEvent(s->stream, s->ev_copy, 0));  // the next upload must not overtake the download
+    F2D_CUDA(cudaStreamSynchronize(s->copy_stream));
     return f2d_sync(s);
 }
 

@@ -27,7 +27,7 @@ class FluidSolverB200:
     """Drop-in for fluid_solver_gpu on one B200 (or one row slab of a multi-GPU run)."""
 
     def __init__(self, rows, cols, diffuse_iters=15, project_iters=20, smooth=True, jacobi_mode=None,
-                 temporal_block=0, divide_mode=capi.DIV_F32_CORR, use_graph=True, device=-1,
+                 temporal_block=0, temporal_block_diffuse=0, divide_mode=capi.DIV_F32_CORR, use_graph=True, device=-1,
                  global_rows=None, row_offset=0, halo=0, stream=None):
         self._h = C.c_void_p()
         L = capi.load()
@@ -39,6 +39,7 @@ class FluidSolverB200:
         if jacobi_mode is not None:
             cfg.jacobi_mode = jacobi_mode
         cfg.temporal_block = temporal_block
+        cfg.temporal_block_diffuse = temporal_block_diffuse
         cfg.divide_mode = divide_mode
         cfg.use_graph = 1 if use_graph else 0
         cfg.device = device

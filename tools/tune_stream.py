@@ -18,11 +18,11 @@ def fields(n):
 
 
 def run(n, k, reps, mode, T, div, env):
-    for key in ("F2D_STREAM_CHUNK_ROWS", "F2D_STREAM_WARPS_PER_CTA", "F2D_STREAM_RHS_SMEM"):
+    for key in ("F2D_STREAM_CHUNK_ROWS", "F2D_STREAM_WARPS_PER_CTA", "F2D_STREAM_RHS_SMEM", "F2D_STREAM_MIN_BLOCKS"):
         os.environ.pop(key, None)
     os.environ.update({a: str(b) for a, b in env.items()})
     d, u, v = FIELDS[n]
-    with f2d.FluidSolverB200(n, n, diffuse_iters=k, project_iters=k, jacobi_mode=mode, temporal_block=T,
+    with f2d.FluidSolverB200(n, n, diffuse_iters=k, project_iters=k, jacobi_mode=mode, temporal_block=T, temporal_block_diffuse=T,
                              divide_mode=div) as s:
         s.upload(d, u, v)
         p_ms = s.bench_jacobi(False, k, reps) / reps
@@ -45,18 +45,13 @@ def main():
     for n in sizes:
         FIELDS[n] = fields(n)
         reps = 3 if n <= 8192 else 1
-        if n <= 8192:
-            run(n, k, reps, 0, 1, 1, {})  # naive
         for T in (1, 2, 4, 8):
             run(n, k, reps, 1, T, 1, {})
+        run(n, k, reps, 1, 8, 1, {"F2D_STREAM_MIN_BLOCKS": 2})
         run(n, k, reps, 1, 4, 1, {"F2D_STREAM_RHS_SMEM": 1})
-        run(n, k, reps, 1, 2, 1, {"F2D_STREAM_RHS_SMEM": 1})
-        for T in (4, 8):
-            for wpc in (2, 8):
-                run(n, k, reps, 1, T, 1, {"F2D_STREAM_WARPS_PER_CTA": wpc})
-            if n <= 8192:
-                for chunk in (48, 64, 96):
-                    run(n, k, reps, 1, T, 1, {"F2D_STREAM_CHUNK_ROWS": chunk})
+        run(n, k, reps, 1, 4, 1, {"F2D_STREAM_RHS_SMEM": 1, "F2D_STREAM_MIN_BLOCKS": 5})
+        run(n, k, reps, 1, 4, 1, {"F2D_STREAM_WARPS_PER_CTA": 2})
+        run(n, k, reps, 1, 8, 1, {"F2D_STREAM_WARPS_PER_CTA": 2})
         FIELDS.pop(n)
     # the unmodified reference GPU solver on the same box ("the kernel to beat"), its own solve()
     try:
