@@ -7,7 +7,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_LIB = os.path.join(_HERE, "libf2d.so")
+_LIB = os.environ.get("F2D_LIB_PATH") or os.path.join(_HERE, "libf2d.so")  # F2D_LIB_PATH: A/B kernel variants
 _HEADER = os.path.join(_ROOT, "include", "f2d.h")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE = 0, 1, 2, 3, 4

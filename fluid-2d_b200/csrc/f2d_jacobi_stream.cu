@@ -36,6 +36,15 @@
 
 #include "f2d_kernels.cuh"
 
+// A/B switches (tools/build_variants.sh builds one library per combination)
+#ifndef F2D_RING_OR
+#define F2D_RING_OR 1   // ring slots addressed as ((row << 9) & mask) | aligned_base on 32-bit shared addresses
+#endif
+#ifndef F2D_SHFL_AHEAD
+#define F2D_SHFL_AHEAD 0  // 1: west/east shuffles issued at the end of the previous row step (costs 2T live
+                          // registers; slower since the row step became one basic block, profiles/ab_r01_run7_*.log)
+#endif
+
 namespace f2d {
 
 namespace {
@@ -69,6 +78,14 @@ struct StreamPlan {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(unsigned smem_addr, const void* gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gmem_src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ float4 lds128(unsigned smem_addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr) : "memory");
+    return v;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void st_global_f4(float* p, const float4& v) {
@@ -117,6 +134,7 @@ struct Ctx {
     float* next;
     float4* ring_p;  // lane-adjusted: + lane
     float4* ring_r;
+    unsigned sp, sr;  // the same two rings as 32-bit shared addresses, each aligned to its own size
     DiffuseCoef coef;
     int pitch, rs, re, y0, y1;
     int cp_bytes;
@@ -145,23 +163,45 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
             const int rl = r + kPFD;
             if (rl <= cx.re) {
                 const size_t off = (size_t)rl * cx.pitch;
+#if F2D_RING_OR
+                if (!PIN_ZERO) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
+                cp_async16_s((((unsigned)rl << 9) & ((RINGR - 1) << 9)) | cx.sr, cx.rhs + off, cx.cp_bytes);
+#else
                 if (!PIN_ZERO) cp_async16(cx.ring_p + (rl & (kRingP - 1)) * kLanes, cx.prev + off, cx.cp_bytes);
                 cp_async16(cx.ring_r + (rl & (RINGR - 1)) * kLanes, cx.rhs + off, cx.cp_bytes);
+#endif
             }
             cp_async_commit();
         }
         // 2. row r has landed (each lane reads back only the 16 bytes it copied itself)
         cp_async_wait<kPFD>();
         if (FAST || r <= cx.re) {  // FAST: past the last input row this re-reads a stale ring slot (harmless)
+#if F2D_RING_OR
+            if (!PIN_ZERO)
+                W[0][m3(k)] = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);
+            else
+                W[0][m3(k)] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RHS_REGS) RH[mrs(k, RS)] = lds128((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sr);
+#else
             if (!PIN_ZERO)
                 W[0][m3(k)] = cx.ring_p[(r & (kRingP - 1)) * kLanes];
             else
                 W[0][m3(k)] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (RHS_REGS) RH[mrs(k, RS)] = cx.ring_r[(r & (RINGR - 1)) * kLanes];
+#endif
         }
+#if !F2D_SHFL_AHEAD
+        // west/east neighbours of the centre rows of all levels (rows produced in the previous step)
+#pragma unroll
+        for (int s = 0; s < T; ++s) {
+            const float4 bb = W[s][m3(k - s - 1)];
+            wl[s] = __shfl_up_sync(0xffffffffu, bb.w, 1);
+            er[s] = __shfl_down_sync(0xffffffffu, bb.x, 1);
+        }
+#endif
 
-        // 3. level s+1 produces row q = r - s - 1 from level s rows q-1, q, q+1; the west/east
-        //    neighbours wl[s], er[s] of the centre row were shuffled at the end of the previous step.
+        // 3. level s+1 produces row q = r - s - 1 from level s rows q-1, q, q+1; wl[s], er[s] are the
+        //    west/east neighbours of the centre row (a row produced in the previous step).
         //    active levels: rs+1 <= q <= re-1  <=>  s_lo <= s <= s_hi
         const int s_lo = r - cx.re, s_hi = r - cx.rs - 2;
         const int s_top = cx.top_dom ? r - 2 : -1;           // level whose q == 1 (global top edge above it)
@@ -178,7 +218,11 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
                 if (RHS_REGS)
                     rhs = RH[mrs(k - s - 1, RS)];
                 else
+#if F2D_RING_OR
+                    rhs = lds128((((unsigned)q << 9) & ((RINGR - 1) << 9)) | cx.sr);
+#else
                     rhs = cx.ring_r[(q & (RINGR - 1)) * kLanes];
+#endif
                 float4 nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
                 // interior rows: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32).  Written as
                 // two predicated selects (no branch) so that a whole row step stays one basic block and
@@ -209,12 +253,14 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
         }
         // 4. the centre row of level s in the NEXT step is row r - s (slot m3(k - s)); it is final now,
         //    so its west/east shuffles are issued here and complete while the next row is fetched
+#if F2D_SHFL_AHEAD
 #pragma unroll
         for (int s = 0; s < T; ++s) {
             const float4 b = W[s][m3(k - s)];
             wl[s] = __shfl_up_sync(0xffffffffu, b.w, 1);
             er[s] = __shfl_down_sync(0xffffffffu, b.x, 1);
         }
+#endif
     }
 }
 
@@ -266,8 +312,22 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     cx.prev = PIN_ZERO ? nullptr : fld.prev + jsafe;
     cx.rhs = fld.rhs + jsafe;
     cx.next = fld.next + jsafe;
+#if F2D_RING_OR
+    {
+        // [ring_r of warp 0 .. wpc-1][ring_p of warp 0 .. wpc-1], the block aligned to the rhs ring size so
+        // that "(row << 9) & mask | base" addresses a slot with two integer instructions
+        constexpr unsigned RB = RINGR * kLanes * 16u, PB = kRingP * kLanes * 16u;
+        const unsigned s0 = ((unsigned)__cvta_generic_to_shared(smem) + RB - 1u) & ~(RB - 1u);
+        cx.sr = s0 + (unsigned)warp_in_cta * RB + (unsigned)lane * 16u;
+        cx.sp = s0 + (unsigned)warps_per_cta * RB + (unsigned)warp_in_cta * PB + (unsigned)lane * 16u;
+        cx.ring_p = nullptr;
+        cx.ring_r = nullptr;
+    }
+#else
     cx.ring_p = smem + (size_t)warp_in_cta * (kRingP + RINGR) * kLanes + lane;
     cx.ring_r = cx.ring_p + kRingP * kLanes;
+    cx.sp = cx.sr = 0;
+#endif
 
     // ---- rows of this warp (local row indices)
     // the first / last chunk are `edge_trim` rows shorter: their edge-rule steps cost more
@@ -309,8 +369,13 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
         const int rl = cx.rs + p;
         if (rl <= cx.re) {
             const size_t off = (size_t)rl * cx.pitch;
+#if F2D_RING_OR
+            if (!PIN_ZERO) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
+            cp_async16_s((((unsigned)rl << 9) & ((RINGR - 1) << 9)) | cx.sr, cx.rhs + off, cx.cp_bytes);
+#else
             if (!PIN_ZERO) cp_async16(cx.ring_p + (rl & (kRingP - 1)) * kLanes, cx.prev + off, cx.cp_bytes);
             cp_async16(cx.ring_r + (rl & (RINGR - 1)) * kLanes, cx.rhs + off, cx.cp_bytes);
+#endif
         }
         cp_async_commit();
     }
@@ -363,7 +428,8 @@ void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, in
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;
     int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
     wpc = std::min(wpc, 4);  // __launch_bounds__(128, ...)
-    const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS)) * kLanes * sizeof(float4);
+    const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS)) * kLanes * sizeof(float4) +
+                        (F2D_RING_OR ? (size_t)ring_r_of(T, RHS_REGS) * kLanes * sizeof(float4) : 0);  // alignment slack
     static int occ_cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (occ_cache[wpc] == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
