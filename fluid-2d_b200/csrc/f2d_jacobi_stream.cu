@@ -37,9 +37,6 @@
 #include "f2d_kernels.cuh"
 
 // A/B switches (tools/build_variants.sh builds one library per combination)
-#ifndef F2D_RING_OR
-#define F2D_RING_OR 1   // ring slots addressed as ((row << 9) & mask) | aligned_base on 32-bit shared addresses
-#endif
 #ifndef F2D_SHFL_AHEAD
 #define F2D_SHFL_AHEAD 0  // 1: west/east shuffles issued at the end of the previous row step (costs 2T live
                           // registers; slower since the row step became one basic block, profiles/ab_r01_run7_*.log)
@@ -75,10 +72,6 @@ struct StreamPlan {
     int chunks[2], chunk_rows[2], edge_trim[2];
 };
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem_src), "r"(src_bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async16_s(unsigned smem_addr, const void* gmem_src, int src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_addr), "l"(gmem_src), "r"(src_bytes) : "memory");
 }
@@ -86,6 +79,9 @@ __device__ __forceinline__ float4 lds128(unsigned smem_addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr) : "memory");
     return v;
+}
+__device__ __forceinline__ void sts128(unsigned smem_addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(smem_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void st_global_f4(float* p, const float4& v) {
@@ -132,9 +128,11 @@ struct Ctx {
     const float* prev;  // lane-adjusted: + column of this lane
     const float* rhs;
     float* next;
-    float4* ring_p;  // lane-adjusted: + lane
-    float4* ring_r;
-    unsigned sp, sr;  // the same two rings as 32-bit shared addresses, each aligned to its own size
+    unsigned sp, sr;  // the two async-copy rings as 32-bit shared addresses (lane offset included), each
+                      // aligned to its own size so that a slot is ((row << 9) & mask) | base
+    unsigned sd;      // fused divergence: ring of computed divergence rows (the relaxation's rhs)
+    float* aux;       // fused divergence: the divergence field written for the later passes
+    float mhalf_h;    // fused divergence: -0.5f * h
     DiffuseCoef coef;
     int pitch, rs, re, y0, y1;
     int cp_bytes;
@@ -149,9 +147,13 @@ struct Ctx {
 // feed cells outside the dependency cone of the rows this warp stores, and the store itself is
 // predicated on the owned row range.  Only blocks in which a level meets a GLOBAL top or bottom edge
 // row (edge rule, corner carry) take the checked path (FAST == false).
-template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS, bool FAST, int RS, int RINGR, int NRH>
+template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool FAST, int RS, int RINGR, int NRH>
 __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, float4 (&W)[T][3], float4 (&RH)[NRH],
-                                          float4& out_prev, float (&wl)[T], float (&er)[T]) {
+                                          float4& out_prev, float (&wl)[T], float (&er)[T], float4 (&UV)[2][3]) {
+    // PIN_ZERO == 2: the first pressure pass with the divergence fused in (gpu.cu:164-177 + :376): the two
+    // async rings carry u and v rows instead of iterate and rhs; the rhs row r-1 is computed on the fly
+    constexpr bool FUSE = (PIN_ZERO == 2);
+    constexpr unsigned MASKR = FUSE ? ((kRingP - 1) << 9) : ((RINGR - 1) << 9);  // v rows only need the landing zone
 #pragma unroll
     for (int k = 0; k < RS; ++k) {
         const int rr = rb + k;
@@ -163,32 +165,52 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
             const int rl = r + kPFD;
             if (rl <= cx.re) {
                 const size_t off = (size_t)rl * cx.pitch;
-#if F2D_RING_OR
-                if (!PIN_ZERO) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
-                cp_async16_s((((unsigned)rl << 9) & ((RINGR - 1) << 9)) | cx.sr, cx.rhs + off, cx.cp_bytes);
-#else
-                if (!PIN_ZERO) cp_async16(cx.ring_p + (rl & (kRingP - 1)) * kLanes, cx.prev + off, cx.cp_bytes);
-                cp_async16(cx.ring_r + (rl & (RINGR - 1)) * kLanes, cx.rhs + off, cx.cp_bytes);
-#endif
+                if (!PIN_ZERO || FUSE) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
+                cp_async16_s((((unsigned)rl << 9) & MASKR) | cx.sr, cx.rhs + off, cx.cp_bytes);
             }
             cp_async_commit();
         }
         // 2. row r has landed (each lane reads back only the 16 bytes it copied itself)
         cp_async_wait<kPFD>();
         if (FAST || r <= cx.re) {  // FAST: past the last input row this re-reads a stale ring slot (harmless)
-#if F2D_RING_OR
             if (!PIN_ZERO)
                 W[0][m3(k)] = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);
             else
                 W[0][m3(k)] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (RHS_REGS) RH[mrs(k, RS)] = lds128((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sr);
-#else
-            if (!PIN_ZERO)
-                W[0][m3(k)] = cx.ring_p[(r & (kRingP - 1)) * kLanes];
+            if (FUSE) {
+                UV[0][m3(k)] = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);  // u row r
+                UV[1][m3(k)] = lds128((((unsigned)r << 9) & MASKR) | cx.sr);                // v row r
+            } else if (RHS_REGS) {
+                RH[mrs(k, RS)] = lds128((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sr);
+            }
+        }
+        if (FUSE) {
+            // divergence of row r-1 from u[r-1] (with its west/east neighbours) and v[r], v[r-2]
+            const float4 uc = UV[0][m3(k - 1)], vs = UV[1][m3(k)], vn = UV[1][m3(k - 2)];
+            const float ul = __shfl_up_sync(0xffffffffu, uc.w, 1);
+            const float ur = __shfl_down_sync(0xffffffffu, uc.x, 1);
+            float4 dv;
+            dv.x = divergence_update(uc.y, ul, vs.x, vn.x, cx.mhalf_h);
+            dv.y = divergence_update(uc.z, uc.x, vs.y, vn.y, cx.mhalf_h);
+            dv.z = divergence_update(uc.w, uc.y, vs.z, vn.z, cx.mhalf_h);
+            dv.w = divergence_update(ur, uc.z, vs.w, vn.w, cx.mhalf_h);
+            // set_boundary_continuous on the divergence (gpu.cu:376): edge columns copy their neighbour
+            dv.x = cx.has_left ? dv.y : dv.x;
+            dv.w = cx.has_right ? dv.z : dv.w;
+            const int qd = r - 1;
+            if (RHS_REGS)
+                RH[mrs(k - 1, RS)] = dv;
             else
-                W[0][m3(k)] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (RHS_REGS) RH[mrs(k, RS)] = cx.ring_r[(r & (RINGR - 1)) * kLanes];
-#endif
+                sts128((((unsigned)qd << 9) & ((RINGR - 1) << 9)) | cx.sd, dv);
+            if (cx.own_x && qd >= cx.rs + 1 && qd <= cx.re - 1) {
+                if (qd >= cx.y0 && qd < cx.y1) st_global_f4(cx.aux + (size_t)qd * cx.pitch, dv);
+                // the edge rows of the stored field copy the adjacent interior row, corners are the memset zeros
+                float4 e = dv;
+                e.x = cx.has_left ? 0.f : e.x;
+                e.w = cx.has_right ? 0.f : e.w;
+                if (qd == 1 && cx.top_dom && cx.y0 == 0) st_global_f4(cx.aux, e);
+                if (qd == cx.re - 1 && cx.bot_dom) st_global_f4(cx.aux + (size_t)cx.re * cx.pitch, e);
+            }
         }
 #if !F2D_SHFL_AHEAD
         // west/east neighbours of the centre rows of all levels (rows produced in the previous step)
@@ -218,11 +240,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
                 if (RHS_REGS)
                     rhs = RH[mrs(k - s - 1, RS)];
                 else
-#if F2D_RING_OR
-                    rhs = lds128((((unsigned)q << 9) & ((RINGR - 1) << 9)) | cx.sr);
-#else
-                    rhs = cx.ring_r[(q & (RINGR - 1)) * kLanes];
-#endif
+                    rhs = lds128((((unsigned)q << 9) & ((RINGR - 1) << 9)) | (FUSE ? cx.sd : cx.sr));
                 float4 nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
                 // interior rows: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32).  Written as
                 // two predicated selects (no branch) so that a whole row step stays one basic block and
@@ -265,7 +283,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
 }
 
 // MINB = resident CTAs (of 128 threads) per SM the register allocator must allow
-template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS, int MINB>
+template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch batch, StreamPlan plan) {
     constexpr int HALO = halo_of(T);
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;  // unroll factor of the row loop
@@ -309,25 +327,27 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     cx.own_x = in_dom && (lane >= HALO / 4) && (lane < kLanes - HALO / 4);
     cx.cp_bytes = in_dom ? 16 : 0;
     const int jsafe = in_dom ? jb : 0;
-    cx.prev = PIN_ZERO ? nullptr : fld.prev + jsafe;
+    cx.prev = (PIN_ZERO == 1) ? nullptr : fld.prev + jsafe;  // PIN_ZERO == 2: u
+    cx.aux = (PIN_ZERO == 2) ? fld.aux + jsafe : nullptr;
+    cx.mhalf_h = fld.coef.a;  // fused divergence: the launcher passes -0.5f*h here
     cx.rhs = fld.rhs + jsafe;
     cx.next = fld.next + jsafe;
-#if F2D_RING_OR
     {
         // [ring_r of warp 0 .. wpc-1][ring_p of warp 0 .. wpc-1], the block aligned to the rhs ring size so
         // that "(row << 9) & mask | base" addresses a slot with two integer instructions
         constexpr unsigned RB = RINGR * kLanes * 16u, PB = kRingP * kLanes * 16u;
         const unsigned s0 = ((unsigned)__cvta_generic_to_shared(smem) + RB - 1u) & ~(RB - 1u);
-        cx.sr = s0 + (unsigned)warp_in_cta * RB + (unsigned)lane * 16u;
-        cx.sp = s0 + (unsigned)warps_per_cta * RB + (unsigned)warp_in_cta * PB + (unsigned)lane * 16u;
-        cx.ring_p = nullptr;
-        cx.ring_r = nullptr;
+        if (PIN_ZERO == 2) {
+            // fused divergence: [divergence ring (RB) x wpc][v landing ring (PB) x wpc][u landing ring (PB) x wpc]
+            cx.sd = s0 + (unsigned)warp_in_cta * RB + (unsigned)lane * 16u;
+            cx.sr = s0 + (unsigned)warps_per_cta * RB + (unsigned)warp_in_cta * PB + (unsigned)lane * 16u;
+            cx.sp = s0 + (unsigned)warps_per_cta * (RB + PB) + (unsigned)warp_in_cta * PB + (unsigned)lane * 16u;
+        } else {
+            cx.sd = 0;
+            cx.sr = s0 + (unsigned)warp_in_cta * RB + (unsigned)lane * 16u;
+            cx.sp = s0 + (unsigned)warps_per_cta * RB + (unsigned)warp_in_cta * PB + (unsigned)lane * 16u;
+        }
     }
-#else
-    cx.ring_p = smem + (size_t)warp_in_cta * (kRingP + RINGR) * kLanes + lane;
-    cx.ring_r = cx.ring_p + kRingP * kLanes;
-    cx.sp = cx.sr = 0;
-#endif
 
     // ---- rows of this warp (local row indices)
     // the first / last chunk are `edge_trim` rows shorter: their edge-rule steps cost more
@@ -354,6 +374,9 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     float4 RH[NRH];
     float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
     float wl[T], er[T];
+    float4 UV[2][3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) UV[0][m] = UV[1][m] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < T; ++s) {
         wl[s] = er[s] = 0.f;
@@ -369,13 +392,8 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
         const int rl = cx.rs + p;
         if (rl <= cx.re) {
             const size_t off = (size_t)rl * cx.pitch;
-#if F2D_RING_OR
-            if (!PIN_ZERO) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
-            cp_async16_s((((unsigned)rl << 9) & ((RINGR - 1) << 9)) | cx.sr, cx.rhs + off, cx.cp_bytes);
-#else
-            if (!PIN_ZERO) cp_async16(cx.ring_p + (rl & (kRingP - 1)) * kLanes, cx.prev + off, cx.cp_bytes);
-            cp_async16(cx.ring_r + (rl & (RINGR - 1)) * kLanes, cx.rhs + off, cx.cp_bytes);
-#endif
+            if (PIN_ZERO != 1) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
+            cp_async16_s((((unsigned)rl << 9) & ((PIN_ZERO == 2 ? kRingP - 1 : RINGR - 1) << 9)) | cx.sr, cx.rhs + off, cx.cp_bytes);
         }
         cp_async_commit();
     }
@@ -384,9 +402,9 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
         const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
         const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
         if (!edge_block)
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er);
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
         else
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er);
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
     }
     cp_async_wait<0>();
 }
@@ -422,14 +440,14 @@ inline ClassPlan plan_class(int rows, int T, int RS, double cost_budget, double 
     return cp;
 }
 
-template <int T, bool DIFFUSE, int DIVMODE, bool PIN_ZERO, bool RHS_REGS, int MINB>
+template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, int MINB>
 void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, int sm_count, cudaStream_t st) {
     auto kern = k_jacobi_stream<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, MINB>;
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;
     int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
     wpc = std::min(wpc, 4);  // __launch_bounds__(128, ...)
-    const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS)) * kLanes * sizeof(float4) +
-                        (F2D_RING_OR ? (size_t)ring_r_of(T, RHS_REGS) * kLanes * sizeof(float4) : 0);  // alignment slack
+    const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS) + (PIN_ZERO == 2 ? kRingP : 0)) * kLanes * sizeof(float4) +
+                        (size_t)ring_r_of(T, RHS_REGS) * kLanes * sizeof(float4);  // alignment slack
     static int occ_cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (occ_cache[wpc] == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -480,14 +498,16 @@ template <int T, bool RHS_REGS, int MINB>
 void launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, const StreamTuning& tune, int sm_count,
               cudaStream_t st) {
     if (!diffuse) {
-        if (b.f[0].prev == nullptr)
-            launch_one<T, false, F2D_DIV_F64, true, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        if (b.f[0].aux != nullptr)  // first pressure pass with the divergence fused in: prev = u, rhs = v
+            launch_one<T, false, F2D_DIV_F64, 2, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        else if (b.f[0].prev == nullptr)
+            launch_one<T, false, F2D_DIV_F64, 1, RHS_REGS, MINB>(g, b, tune, sm_count, st);
         else
-            launch_one<T, false, F2D_DIV_F64, false, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+            launch_one<T, false, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     } else if (divmode == F2D_DIV_F64) {
-        launch_one<T, true, F2D_DIV_F64, false, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        launch_one<T, true, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     } else {
-        launch_one<T, true, F2D_DIV_F32_CORR, false, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        launch_one<T, true, F2D_DIV_F32_CORR, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     }
 }
 

@@ -11,6 +11,7 @@ struct RelaxField {
     const float* prev;  // iterate k   (nullptr: identically zero -- first pressure pass)
     const float* rhs;   // x0 (diffuse) or divergence (pressure)
     float* next;        // iterate k + sweeps
+    float* aux;         // fused-divergence first pressure pass: prev = u, rhs = v, aux = divergence out; else nullptr
     int kind;           // F2D_BND_*
     DiffuseCoef coef;   // diffuse only
 };

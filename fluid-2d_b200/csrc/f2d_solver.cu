@@ -93,6 +93,7 @@ struct f2d_solver {
     cudaEvent_t ev_density = nullptr, ev_copy = nullptr;
     bool capturing = false;
     bool host_register = true;
+    bool fuse_divergence = true;  // F2D_FUSE_DIVERGENCE=0: separate divergence kernel (A/B, cross-check)
     std::vector<void*> registered;  // host ranges this solver page-locked (cudaHostRegister)
 
     // ---- scratch pool -------------------------------------------------------------------
@@ -248,6 +249,7 @@ struct f2d_solver {
                 b.f[i].prev = cur[i];
                 b.f[i].rhs = rhs[i];
                 b.f[i].next = flip ? pong[i] : ping[i];
+                b.f[i].aux = nullptr;
                 b.f[i].kind = kinds[i];
                 b.f[i].coef = coefs ? coefs[i] : DiffuseCoef{0.f, 0.f, 0.f, 0.f, 1.0};
             }
@@ -279,15 +281,44 @@ struct f2d_solver {
         last_div = last_p = nullptr;
         float* dv = acquire();
         if (!dv) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-        F2D_TRY(need({{u_in, H() - 1}, {v_in, H() - 1}}));  // radius-1 stencil
-        launch_divergence(g, u_in, v_in, dv, h(), stream);
-        count();
-        set_inv(dv, std::max(get_inv(u_in), get_inv(v_in)) + 1);
         const float* pin[1] = {nullptr};
         const float* prhs[1] = {dv};
         const int kind[1] = {F2D_BND_CONTINUOUS};
         const float* pout[1];
-        F2D_TRY(relax(1, pin, prhs, kind, nullptr, false, K, pout));
+        uint32_t k_left = K;
+        float* p1 = nullptr;
+        if (cfg.jacobi_mode == F2D_JACOBI_STREAM && K > 0 && fuse_divergence) {
+            // the divergence is computed inside the first pressure pass (p0 == 0, so sweep 1 is 0.25*div):
+            // the pass streams u and v, writes the divergence field for the later passes and p after T sweeps
+            uint32_t T = cfg.temporal_block;
+            while (T > K) T >>= 1;
+            if (multi() && (int)T > H()) return fail(F2D_ERR_INVALID, "halo (%d) shallower than temporal_block (%u)", H(), T);
+            F2D_TRY(need({{u_in, H() - (int)T}, {v_in, H() - (int)T}}));
+            p1 = acquire();
+            if (!p1) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+            RelaxBatch b;
+            b.n = 1;
+            b.f[0].prev = u_in;
+            b.f[0].rhs = v_in;
+            b.f[0].next = p1;
+            b.f[0].aux = dv;
+            b.f[0].kind = F2D_BND_CONTINUOUS;
+            b.f[0].coef = DiffuseCoef{-0.5f * h(), 0.f, 0.f, 0.f, 1.0};
+            launch_jacobi_stream(g, b, false, (int)cfg.divide_mode, (int)T, (int)T, tune, sm_count, stream);
+            count();
+            const int iuv = std::max(get_inv(u_in), get_inv(v_in));
+            set_inv(dv, iuv + 1);
+            set_inv(p1, iuv + (int)T);
+            pin[0] = p1;
+            k_left = K - T;
+        } else {
+            F2D_TRY(need({{u_in, H() - 1}, {v_in, H() - 1}}));  // radius-1 stencil
+            launch_divergence(g, u_in, v_in, dv, h(), stream);
+            count();
+            set_inv(dv, std::max(get_inv(u_in), get_inv(v_in)) + 1);
+        }
+        F2D_TRY(relax(1, pin, prhs, kind, nullptr, false, k_left, pout));
+        if (p1 && pout[0] != p1) release(p1);
         F2D_TRY(need({{pout[0], H() - 1}}));
         launch_gradient(g, pout[0], u_in, v_in, u_out, v_out, h(), stream);
         count();
@@ -755,6 +786,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     s->tune.warps_per_cta = env_int("F2D_STREAM_WARPS_PER_CTA", 0);
     s->tune.rhs_in_smem = env_int("F2D_STREAM_RHS_SMEM", 0);
     s->tune.min_blocks = env_int("F2D_STREAM_MIN_BLOCKS", 0);
+    s->fuse_divergence = env_int("F2D_FUSE_DIVERGENCE", 1) != 0;
 
     auto cleanup = [&](int rc) {
         f2d_destroy(s);
