@@ -1,0 +1,83 @@
+// simulation_headless.hpp -- the reference's `simulation` class without SFML.
+// Mirrors the caller contract around fluid_solver::solve: six host grids owned by the simulation
+// (src/simulation.hpp:64-77), source injection scaled by width*height (src/simulation.cpp:44-51),
+// update() = solve() then zero the sources (src/simulation.cpp:53-65), reset() zeroes the state
+// (src/simulation.cpp:29-34), solver chosen by an enum (src/simulation.hpp:14, src/simulation.cpp:17-26).
+// The draw()/coordinates_to_cell() halves of the reference class are renderer concerns and not here.
+#pragma once
+
+#include <algorithm>
+#include <chrono>
+#include <memory>
+#include <stdexcept>
+
+#include "fluid_solver.hpp"
+#include "fluid_solver_b200.hpp"
+
+enum class solver_type { b200 };  // the reference's enumerators are { gpu, cpu }; see INTEGRATION.md for the merged switch
+
+struct simulation_config {
+    size_t width = 800;             // src/app.cpp:30-31
+    size_t height = 800;
+    solver_type solver = solver_type::b200;
+    float diffusion_rate = 0.5f;    // src/app.cpp:33
+    float viscosity = 1e-6f;        // src/app.cpp:34
+    fluid_solver_b200::options solver_options{};
+};
+
+class simulation_headless {
+public:
+    explicit simulation_headless(simulation_config const& config)
+        : m_config(config),
+          m_density_grid{config.height, config.width, 0.f},
+          m_horizontal_velocity_grid{config.height, config.width, 0.f},
+          m_vertical_velocity_grid{config.height, config.width, 0.f},
+          m_horizontal_velocity_source_grid{config.height, config.width, 0.f},
+          m_vertical_velocity_source_grid{config.height, config.width, 0.f},
+          m_density_source_grid{config.height, config.width, 0.f} {
+        switch (config.solver) {
+            case solver_type::b200:
+                m_solver = std::make_unique<fluid_solver_b200>(config.height, config.width, config.solver_options);
+                break;
+        }
+    }
+
+    void reset() {
+        std::fill(m_density_grid.begin(), m_density_grid.end(), 0.f);
+        std::fill(m_horizontal_velocity_grid.begin(), m_horizontal_velocity_grid.end(), 0.f);
+        std::fill(m_vertical_velocity_grid.begin(), m_vertical_velocity_grid.end(), 0.f);
+    }
+
+    void add_density_source(size_t const i, size_t const j, float const value) {
+        m_density_source_grid(i, j) += value * m_config.width * m_config.height;
+    }
+
+    void add_velocity_source(size_t const i, size_t const j, float const horizontal_value, float const vertical_value) {
+        m_horizontal_velocity_source_grid(i, j) += horizontal_value * m_config.width * m_config.height;
+        m_vertical_velocity_source_grid(i, j) += vertical_value * m_config.width * m_config.height;
+    }
+
+    void update(std::chrono::duration<float> const& dt) {
+        m_solver->solve(m_density_grid, m_density_source_grid, m_config.diffusion_rate, m_horizontal_velocity_grid,
+                        m_vertical_velocity_grid, m_horizontal_velocity_source_grid, m_vertical_velocity_source_grid,
+                        m_config.viscosity, dt.count());
+        std::fill(m_density_source_grid.begin(), m_density_source_grid.end(), 0.0f);
+        std::fill(m_horizontal_velocity_source_grid.begin(), m_horizontal_velocity_source_grid.end(), 0.0f);
+        std::fill(m_vertical_velocity_source_grid.begin(), m_vertical_velocity_source_grid.end(), 0.0f);
+    }
+
+    grid<float>& density() { return m_density_grid; }
+    grid<float>& horizontal_velocity() { return m_horizontal_velocity_grid; }
+    grid<float>& vertical_velocity() { return m_vertical_velocity_grid; }
+    simulation_config const& config() const { return m_config; }
+
+private:
+    simulation_config m_config;
+    grid<float> m_density_grid;
+    grid<float> m_horizontal_velocity_grid;
+    grid<float> m_vertical_velocity_grid;
+    grid<float> m_horizontal_velocity_source_grid;
+    grid<float> m_vertical_velocity_source_grid;
+    grid<float> m_density_source_grid;
+    std::unique_ptr<fluid_solver> m_solver;
+};
