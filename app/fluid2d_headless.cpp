@@ -5,7 +5,7 @@
 //
 //   fluid2d_headless [--size N | --width W --height H] [--steps S] [--dt 0.02] [--diffusion 0.5]
 //                    [--viscosity 1e-6] [--kd 15] [--kp 20] [--no-smooth] [--exact-divide]
-//                    [--load prefix] [--dump prefix] [--dump-every K] [--quiet]
+//                    [--load prefix] [--dump prefix] [--dump-every K] [--ppm file.ppm] [--quiet]
 //   --load/--dump use prefix_{density,u,v}.npy (include/f2d_npy.hpp)
 #include <cmath>
 #include <cstdio>
@@ -22,7 +22,7 @@ struct args {
     int steps = 100, dump_every = 0;
     float dt = 0.02f;
     bool quiet = false;
-    std::string load, dump;
+    std::string load, dump, ppm;
     simulation_config cfg;
 };
 
@@ -44,6 +44,7 @@ bool parse(int argc, char** argv, args& a) {
         else if (is("--exact-divide")) a.cfg.solver_options.exact_divide = true;
         else if (is("--load")) { if (!(v = val())) return false; a.load = v; }
         else if (is("--dump")) { if (!(v = val())) return false; a.dump = v; }
+        else if (is("--ppm")) { if (!(v = val())) return false; a.ppm = v; }
         else if (is("--dump-every")) { if (!(v = val())) return false; a.dump_every = std::atoi(v); }
         else if (is("--quiet")) a.quiet = true;
         else return false;
@@ -98,6 +99,7 @@ int main(int argc, char** argv) {
         }
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (!a.dump.empty()) dump(sim, a.dump);
+        if (!a.ppm.empty()) sim.draw_density_ppm(a.ppm, 255.f, 160.f, 64.f);
         double sum = 0, umax = 0;
         for (auto it = sim.density().cbegin(); it != sim.density().cend(); ++it) sum += *it;
         for (auto it = sim.horizontal_velocity().cbegin(); it != sim.horizontal_velocity().cend(); ++it) umax = std::max(umax, std::fabs(static_cast<double>(*it)));

@@ -46,6 +46,11 @@ void launch_smooth_bnd(const Geom& g, const float* in, float* out, bool do_smoot
 void launch_smooth_plain(const Geom& g, const float* in, float* out, cudaStream_t st);
 void launch_set_bnd_inplace(const Geom& g, float* f, int kind, cudaStream_t st);
 
+// ---- headless renderers (f2d_render.cu)
+void launch_density_to_rgba(const Geom& g, const float* d, void* img, float mr, float mg, float mb, cudaStream_t st);
+void launch_velocity_to_lines(const Geom& g, const float* u, const float* v, void* lines, float hscale, float vscale,
+                              float norm, cudaStream_t st);
+
 // ---- temporally blocked streaming relaxation (f2d_jacobi_stream.cu) ------------------------
 struct StreamTuning {
     int chunk_rows;     // output rows per warp (0 = auto)

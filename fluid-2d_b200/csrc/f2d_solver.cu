@@ -93,6 +93,8 @@ struct f2d_solver {
     cudaEvent_t ev_density = nullptr, ev_copy = nullptr;
     bool capturing = false;
     bool host_register = true;
+    void* render_buf = nullptr;  // scratch of the headless renderers
+    size_t render_bytes = 0;
     bool fuse_divergence = true;  // F2D_FUSE_DIVERGENCE=0: separate divergence kernel (A/B, cross-check)
     std::vector<void*> registered;  // host ranges this solver page-locked (cudaHostRegister)
 
@@ -838,6 +840,7 @@ F2D_API void f2d_destroy(f2d_solver* s) {
         if (s->state[i]) cudaFree(s->state[i]);
     for (float* p : s->temps) cudaFree(p);
     if (s->oob_flag) cudaFree(s->oob_flag);
+    if (s->render_buf) cudaFree(s->render_buf);
     if (s->rx_up) cudaFree(s->rx_up);
     if (s->rx_down) cudaFree(s->rx_down);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
@@ -1093,6 +1096,48 @@ F2D_API int f2d_bench_jacobi(f2d_solver* s, int diffuse_like, uint32_t iters, ui
     F2D_CUDA(cudaEventRecord(s->ev1, s->stream));
     F2D_CUDA(cudaEventSynchronize(s->ev1));
     F2D_CUDA(cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1));
+    return F2D_OK;
+}
+
+// ------------------------------------------------------------------------------ renderers
+static int render_common(f2d_solver* s, size_t bytes, void** scratch) {
+    if (s->render_bytes < bytes) {
+        if (s->render_buf) cudaFree(s->render_buf);
+        s->render_buf = nullptr;
+        s->render_bytes = 0;
+        F2D_CUDA(cudaMalloc(&s->render_buf, bytes));
+        s->render_bytes = bytes;
+    }
+    *scratch = s->render_buf;
+    return F2D_OK;
+}
+
+F2D_API int f2d_render_density_rgba(f2d_solver* s, float mult_r, float mult_g, float mult_b, unsigned char* host_rgba) {
+    F2D_NEED(s);
+    if (!host_rgba) return fail(F2D_ERR_INVALID, "NULL argument");
+    const size_t bytes = (size_t)s->g.rows * s->g.cols * 4;
+    void* buf = nullptr;
+    F2D_TRY(render_common(s, bytes, &buf));
+    launch_density_to_rgba(s->g, s->state[F2D_FIELD_DENSITY], buf, mult_r, mult_g, mult_b, s->stream);
+    s->count();
+    F2D_CUDA(cudaGetLastError());
+    F2D_CUDA(cudaMemcpyAsync(host_rgba, buf, bytes, cudaMemcpyDeviceToHost, s->stream));
+    F2D_CUDA(cudaStreamSynchronize(s->stream));
+    return F2D_OK;
+}
+
+F2D_API int f2d_render_velocity_lines(f2d_solver* s, float horizontal_scale, float vertical_scale, float* host_lines) {
+    F2D_NEED(s);
+    if (!host_lines) return fail(F2D_ERR_INVALID, "NULL argument");
+    const size_t bytes = (size_t)s->g.rows * s->g.cols * 4 * sizeof(float);
+    void* buf = nullptr;
+    F2D_TRY(render_common(s, bytes, &buf));
+    launch_velocity_to_lines(s->g, s->state[F2D_FIELD_U], s->state[F2D_FIELD_V], buf, horizontal_scale, vertical_scale,
+                             sqrtf((float)s->global_cells()), s->stream);
+    s->count();
+    F2D_CUDA(cudaGetLastError());
+    F2D_CUDA(cudaMemcpyAsync(host_lines, buf, bytes, cudaMemcpyDeviceToHost, s->stream));
+    F2D_CUDA(cudaStreamSynchronize(s->stream));
     return F2D_OK;
 }
 

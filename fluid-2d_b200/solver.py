@@ -141,6 +141,20 @@ class FluidSolverB200:
     def stage_project(self, iters):
         capi.check(self._L.f2d_stage_project(self._h, iters))
 
+    # ---- headless renderers
+    def render_density_rgba(self, mult=(255.0, 255.0, 255.0)):
+        """density -> RGBA8 image (rows, cols, 4), as grid_to_image_kernel (src/density_grid_renderer.cu:10-29)."""
+        img = np.empty((self.rows, self.cols, 4), np.uint8)
+        capi.check(self._L.f2d_render_density_rgba(self._h, mult[0], mult[1], mult[2], img.ctypes.data_as(C.POINTER(C.c_ubyte))))
+        return img
+
+    def render_velocity_lines(self, horizontal_scale=1.0, vertical_scale=1.0):
+        """(rows, cols, 4) segments (start.x, start.y, end.x, end.y), as velocity_to_lines_kernel
+        (src/velocity_grid_renderer.cu:8-44)."""
+        ln = np.empty((self.rows, self.cols, 4), np.float32)
+        capi.check(self._L.f2d_render_velocity_lines(self._h, horizontal_scale, vertical_scale, ln.ctypes.data_as(_FP)))
+        return ln
+
     # ---- measurement / interop
     def bench_jacobi(self, diffuse_like, iters, reps):
         ms = C.c_float()

@@ -161,6 +161,15 @@ F2D_API int f2d_comm_unique_id(char* id128);
 F2D_API int f2d_comm_init(f2d_solver* s, const char* id128, int rank, int nranks, int cfl_cells);
 F2D_API int f2d_comm_stats(const f2d_solver* s, uint64_t* exchanges);
 
+/* ---- headless renderers (next-row f3; read the device-resident fields, no window system) -------
+ * f2d_render_density_rgba : grid_to_image_kernel (src/density_grid_renderer.cu:10-29): rows*cols RGBA8
+ *                           pixels, channel = uint8(clamp(multiplier * density, 0, 255)), A = 255.
+ * f2d_render_velocity_lines: velocity_to_lines_kernel (src/velocity_grid_renderer.cu:8-44): rows*cols
+ *                           segments as 4 floats (start.x, start.y, end.x, end.y); every 8th row/column
+ *                           the end follows the velocity (250000 * vel / sqrtf(rows*cols)). */
+F2D_API int f2d_render_density_rgba(f2d_solver* s, float mult_r, float mult_g, float mult_b, unsigned char* host_rgba);
+F2D_API int f2d_render_velocity_lines(f2d_solver* s, float horizontal_scale, float vertical_scale, float* host_lines);
+
 /* ---- interop ------------------------------------------------------------------------------- */
 /* device pointer + pitch (in floats) of a state field, for zero-copy views (torch, NCCL halos) */
 F2D_API int f2d_field_ptr(f2d_solver* s, int field, void** device_ptr, size_t* pitch_elems);

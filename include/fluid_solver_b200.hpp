@@ -82,6 +82,14 @@ public:
     void download(grid<float>& d, grid<float>& u, grid<float>& v) {
         check(f2d_download(handle_, d.data(), u.data(), v.data()));
     }
+    // headless renderers on the device-resident state of the last solve()/step()
+    // (grid_to_image_kernel, src/density_grid_renderer.cu:10-29; velocity_to_lines_kernel, src/velocity_grid_renderer.cu:8-44)
+    void render_density_rgba(float r, float g, float b, unsigned char* rgba) {
+        check(f2d_render_density_rgba(handle_, r, g, b, rgba));
+    }
+    void render_velocity_lines(float horizontal_scale, float vertical_scale, float* lines) {
+        check(f2d_render_velocity_lines(handle_, horizontal_scale, vertical_scale, lines));
+    }
     f2d_solver* handle() { return handle_; }
 
 private:

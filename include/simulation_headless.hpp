@@ -9,7 +9,10 @@
 #include <algorithm>
 #include <chrono>
 #include <memory>
+#include <cstdio>
 #include <stdexcept>
+#include <string>
+#include <vector>
 
 #include "fluid_solver.hpp"
 #include "fluid_solver_b200.hpp"
@@ -64,6 +67,20 @@ public:
         std::fill(m_density_source_grid.begin(), m_density_source_grid.end(), 0.0f);
         std::fill(m_horizontal_velocity_source_grid.begin(), m_horizontal_velocity_source_grid.end(), 0.0f);
         std::fill(m_vertical_velocity_source_grid.begin(), m_vertical_velocity_source_grid.end(), 0.0f);
+    }
+
+    // density_grid_renderer::draw without SFML (src/density_grid_renderer.cu:38-56): the density image of the
+    // current state as a binary PPM (P6); colour = clamp(multiplier * density, 0, 255) per channel
+    void draw_density_ppm(std::string const& path, float r = 255.f, float g = 255.f, float b = 255.f) {
+        auto* solver = dynamic_cast<fluid_solver_b200*>(m_solver.get());
+        if (!solver) throw std::runtime_error("draw_density_ppm needs the b200 solver");
+        std::vector<unsigned char> rgba(m_config.width * m_config.height * 4);
+        solver->render_density_rgba(r, g, b, rgba.data());
+        FILE* f = std::fopen(path.c_str(), "wb");
+        if (!f) throw std::runtime_error("cannot open " + path);
+        std::fprintf(f, "P6\n%zu %zu\n255\n", m_config.width, m_config.height);
+        for (size_t p = 0; p < m_config.width * m_config.height; ++p) std::fwrite(&rgba[4 * p], 1, 3, f);
+        std::fclose(f);
     }
 
     grid<float>& density() { return m_density_grid; }

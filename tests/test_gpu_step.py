@@ -132,3 +132,31 @@ def test_live_against_unmodified_reference_gpu_solver(f2d, gpu_ok):
         pd, pu, pv = run_steps(f2d, f, 15, 20, 2)
         for name, a, b in (("d", pd, rd), ("u", pu, ru), ("v", pv, rv)):
             assert_close(a, b, "default %s n=%d" % (name, n), rel_l2=4e-6, max_abs_rel=4e-5)
+
+
+def test_headless_renderers_match_restatement(f2d, gpu_ok):
+    """density -> RGBA8 (src/density_grid_renderer.cu:10-29) and velocity -> line list
+    (src/velocity_grid_renderer.cu:8-44) on the device-resident fields, against a numpy restatement
+    (the reference renderers need SFML and cannot be compiled here: parity unpinned)."""
+    n = 72
+    d, u, v, *_ = rng_fields(n, 77)
+    d = (d * np.float32(3.0) - np.float32(0.5)).astype(np.float32)  # exercise both clamps
+    with f2d.FluidSolverB200(n, n) as s:
+        s.upload(d, u, v)
+        img = s.render_density_rgba((255.0, 160.0, 64.0))
+        ln = s.render_velocity_lines(10.0, 7.5)
+    for c, m in enumerate((255.0, 160.0, 64.0)):
+        want = np.clip(np.float32(m) * d, np.float32(0), np.float32(255)).astype(np.uint8)
+        assert np.array_equal(img[:, :, c], want)
+    assert (img[:, :, 3] == 255).all()
+    jj, ii = np.meshgrid(np.arange(n, dtype=np.float32), np.arange(n, dtype=np.float32))
+    sx, sy = jj * np.float32(10.0), ii * np.float32(7.5)
+    ex, ey = sx.copy(), sy.copy()
+    norm = np.sqrt(np.float32(n * n))
+    sel = (np.arange(n) % 8 == 0)
+    m = np.outer(sel, sel)
+    ex[m] = ex[m] + (np.float32(250000.0) * u[m]) / norm
+    ey[m] = ey[m] + (np.float32(250000.0) * v[m]) / norm
+    assert np.array_equal(ln[:, :, 0], sx) and np.array_equal(ln[:, :, 1], sy)
+    assert_bitwise(np.ascontiguousarray(ln[:, :, 2]), ex, "line end x")
+    assert_bitwise(np.ascontiguousarray(ln[:, :, 3]), ey, "line end y")
