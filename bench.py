@@ -219,6 +219,14 @@ def run_single_gpu(args, workload):
     cpu_value = n_s * n_s / cpu_t
 
     bps = step_bytes(kd, kp)
+    # real DRAM traffic per launch of the dominant kernel: from the committed ncu capture of this workload
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))["k_jacobi_stream_pressure"]
+        if tr["grid"] == n and tr["temporal_block"] == T:
+            traffic, traffic_src = tr["dram_bytes_per_launch"], tr["source"]
+    except (OSError, KeyError, ValueError):
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": workload["scaling"], "vs_baseline": None,
@@ -229,7 +237,8 @@ def run_single_gpu(args, workload):
                    "cuda_graph": bool(cfg.use_graph),
                    "l2": "inputs larger than L2 (>= 13 fields x %.0f MiB)" % (cells * 4 / 2**20)},
         "roofline": {"bound": "hbm", "kernel": "k_jacobi_stream (pressure relaxation, %d sweeps per launch)" % T,
-                     "achieved": jac_gbs, "peak": peak, "unit": "GB/s", "frac": jac_gbs / peak, "traffic": None,
+                     "achieved": jac_gbs, "peak": peak, "unit": "GB/s", "frac": jac_gbs / peak, "traffic": traffic,
+                     "traffic_source": traffic_src, "algorithmic_bytes_per_launch": 12.0 * cells * T,
                      "peak_source": peak_src, "algorithmic_bytes_per_cell_sweep": 12,
                      "avg_launch_ms": jac_ms / passes, "launches_timed": passes,
                      "diffuse_kernel": {"achieved": dif_gbs, "frac": dif_gbs / peak, "sweeps_per_launch": Td},

@@ -132,7 +132,8 @@ struct Ctx {
                       // aligned to its own size so that a slot is ((row << 9) & mask) | base
     unsigned sd;      // fused divergence: ring of computed divergence rows (the relaxation's rhs)
     float* aux;       // fused divergence: the divergence field written for the later passes
-    float mhalf_h;    // fused divergence: -0.5f * h
+    float mhalf_h;    // fused divergence: -0.5f * h; fused add_sources: dt
+    int row_top, row_bot;  // local index of the global top / bottom edge row (or out of range)
     DiffuseCoef coef;
     int pitch, rs, re, y0, y1;
     int cp_bytes;
@@ -153,7 +154,11 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
     // PIN_ZERO == 2: the first pressure pass with the divergence fused in (gpu.cu:164-177 + :376): the two
     // async rings carry u and v rows instead of iterate and rhs; the rhs row r-1 is computed on the fly
     constexpr bool FUSE = (PIN_ZERO == 2);
-    constexpr unsigned MASKR = FUSE ? ((kRingP - 1) << 9) : ((RINGR - 1) << 9);  // v rows only need the landing zone
+    // PIN_ZERO == 3: the first diffuse pass with add_sources fused in (gpu.cu:56-67 folded into :290-312): the
+    // rings carry the field and its source; x0 = FMA(dt, s, f) is formed per row, used as iterate AND rhs,
+    // and written out as the rhs of the later passes
+    constexpr bool FSRC = (PIN_ZERO == 3);
+    constexpr unsigned MASKR = (FUSE || FSRC) ? ((kRingP - 1) << 9) : ((RINGR - 1) << 9);  // landing zone only
 #pragma unroll
     for (int k = 0; k < RS; ++k) {
         const int rr = rb + k;
@@ -165,7 +170,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
             const int rl = r + kPFD;
             if (rl <= cx.re) {
                 const size_t off = (size_t)rl * cx.pitch;
-                if (!PIN_ZERO || FUSE) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
+                if (PIN_ZERO != 1) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
                 cp_async16_s((((unsigned)rl << 9) & MASKR) | cx.sr, cx.rhs + off, cx.cp_bytes);
             }
             cp_async_commit();
@@ -173,11 +178,27 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
         // 2. row r has landed (each lane reads back only the 16 bytes it copied itself)
         cp_async_wait<kPFD>();
         if (FAST || r <= cx.re) {  // FAST: past the last input row this re-reads a stale ring slot (harmless)
-            if (!PIN_ZERO)
+            if (FSRC) {
+                const float4 f4 = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);
+                const float4 s4 = lds128((((unsigned)r << 9) & MASKR) | cx.sr);
+                const bool row_in = (r != cx.row_top) && (r != cx.row_bot);  // global interior row
+                float4 x0;
+                x0.x = (row_in && !cx.has_left) ? __fmaf_rn(cx.mhalf_h, s4.x, f4.x) : f4.x;  // mhalf_h carries dt here
+                x0.y = row_in ? __fmaf_rn(cx.mhalf_h, s4.y, f4.y) : f4.y;
+                x0.z = row_in ? __fmaf_rn(cx.mhalf_h, s4.z, f4.z) : f4.z;
+                x0.w = (row_in && !cx.has_right) ? __fmaf_rn(cx.mhalf_h, s4.w, f4.w) : f4.w;
+                W[0][m3(k)] = x0;
+                if (RHS_REGS)
+                    RH[mrs(k, RS)] = x0;
+                else
+                    sts128((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sd, x0);
+                if (cx.own_x && r >= cx.y0 && r < cx.y1 && r <= cx.re) st_global_f4(cx.aux + (size_t)r * cx.pitch, x0);
+            } else if (!PIN_ZERO)
                 W[0][m3(k)] = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);
             else
                 W[0][m3(k)] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (FUSE) {
+            if (FSRC) {
+            } else if (FUSE) {
                 UV[0][m3(k)] = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);  // u row r
                 UV[1][m3(k)] = lds128((((unsigned)r << 9) & MASKR) | cx.sr);                // v row r
             } else if (RHS_REGS) {
@@ -240,7 +261,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
                 if (RHS_REGS)
                     rhs = RH[mrs(k - s - 1, RS)];
                 else
-                    rhs = lds128((((unsigned)q << 9) & ((RINGR - 1) << 9)) | (FUSE ? cx.sd : cx.sr));
+                    rhs = lds128((((unsigned)q << 9) & ((RINGR - 1) << 9)) | ((FUSE || FSRC) ? cx.sd : cx.sr));
                 float4 nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
                 // interior rows: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32).  Written as
                 // two predicated selects (no branch) so that a whole row step stays one basic block and
@@ -328,8 +349,10 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     cx.cp_bytes = in_dom ? 16 : 0;
     const int jsafe = in_dom ? jb : 0;
     cx.prev = (PIN_ZERO == 1) ? nullptr : fld.prev + jsafe;  // PIN_ZERO == 2: u
-    cx.aux = (PIN_ZERO == 2) ? fld.aux + jsafe : nullptr;
-    cx.mhalf_h = fld.coef.a;  // fused divergence: the launcher passes -0.5f*h here
+    cx.aux = (PIN_ZERO >= 2) ? fld.aux + jsafe : nullptr;
+    cx.mhalf_h = (PIN_ZERO == 3) ? batch.dt : fld.coef.a;  // fused divergence: the launcher passes -0.5f*h in coef.a
+    cx.row_top = (g.grow0 == 0) ? 0 : -1;
+    cx.row_bot = g.grows - 1 - g.grow0;
     cx.rhs = fld.rhs + jsafe;
     cx.next = fld.next + jsafe;
     {
@@ -337,8 +360,8 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
         // that "(row << 9) & mask | base" addresses a slot with two integer instructions
         constexpr unsigned RB = RINGR * kLanes * 16u, PB = kRingP * kLanes * 16u;
         const unsigned s0 = ((unsigned)__cvta_generic_to_shared(smem) + RB - 1u) & ~(RB - 1u);
-        if (PIN_ZERO == 2) {
-            // fused divergence: [divergence ring (RB) x wpc][v landing ring (PB) x wpc][u landing ring (PB) x wpc]
+        if (PIN_ZERO >= 2) {
+            // fused divergence / add_sources: [computed rhs ring (RB) x wpc][landing ring (PB) x wpc][landing ring (PB) x wpc]
             cx.sd = s0 + (unsigned)warp_in_cta * RB + (unsigned)lane * 16u;
             cx.sr = s0 + (unsigned)warps_per_cta * RB + (unsigned)warp_in_cta * PB + (unsigned)lane * 16u;
             cx.sp = s0 + (unsigned)warps_per_cta * (RB + PB) + (unsigned)warp_in_cta * PB + (unsigned)lane * 16u;
@@ -393,7 +416,7 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
         if (rl <= cx.re) {
             const size_t off = (size_t)rl * cx.pitch;
             if (PIN_ZERO != 1) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
-            cp_async16_s((((unsigned)rl << 9) & ((PIN_ZERO == 2 ? kRingP - 1 : RINGR - 1) << 9)) | cx.sr, cx.rhs + off, cx.cp_bytes);
+            cp_async16_s((((unsigned)rl << 9) & ((PIN_ZERO >= 2 ? kRingP - 1 : RINGR - 1) << 9)) | cx.sr, cx.rhs + off, cx.cp_bytes);
         }
         cp_async_commit();
     }
@@ -446,7 +469,7 @@ void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, in
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;
     int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
     wpc = std::min(wpc, 4);  // __launch_bounds__(128, ...)
-    const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS) + (PIN_ZERO == 2 ? kRingP : 0)) * kLanes * sizeof(float4) +
+    const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS) + (PIN_ZERO >= 2 ? kRingP : 0)) * kLanes * sizeof(float4) +
                         (size_t)ring_r_of(T, RHS_REGS) * kLanes * sizeof(float4);  // alignment slack
     static int occ_cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (occ_cache[wpc] == 0) {
@@ -505,9 +528,15 @@ void launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, con
         else
             launch_one<T, false, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     } else if (divmode == F2D_DIV_F64) {
-        launch_one<T, true, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        if (b.f[0].aux != nullptr)  // first diffuse pass with add_sources fused in: prev = field, rhs = source
+            launch_one<T, true, F2D_DIV_F64, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        else
+            launch_one<T, true, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     } else {
-        launch_one<T, true, F2D_DIV_F32_CORR, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        if (b.f[0].aux != nullptr)
+            launch_one<T, true, F2D_DIV_F32_CORR, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        else
+            launch_one<T, true, F2D_DIV_F32_CORR, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     }
 }
 

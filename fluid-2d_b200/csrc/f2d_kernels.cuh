@@ -11,13 +11,15 @@ struct RelaxField {
     const float* prev;  // iterate k   (nullptr: identically zero -- first pressure pass)
     const float* rhs;   // x0 (diffuse) or divergence (pressure)
     float* next;        // iterate k + sweeps
-    float* aux;         // fused-divergence first pressure pass: prev = u, rhs = v, aux = divergence out; else nullptr
+    float* aux;         // fused first passes, else nullptr.  pressure: prev = u, rhs = v, aux = divergence out;
+                        // diffuse: prev = field, rhs = source, aux = x0 out (the field after add_sources)
     int kind;           // F2D_BND_*
     DiffuseCoef coef;   // diffuse only
 };
 struct RelaxBatch {
     RelaxField f[kMaxBatch];
     int n;
+    float dt;  // fused add_sources first diffuse pass (aux != nullptr, prev = field, rhs = source): x0 = FMA(dt, s, f)
 };
 
 struct AddSourceBatch {

@@ -95,6 +95,7 @@ struct f2d_solver {
     bool host_register = true;
     void* render_buf = nullptr;  // scratch of the headless renderers
     size_t render_bytes = 0;
+    bool fuse_sources = true;     // F2D_FUSE_SOURCES=0: separate add_sources kernel (A/B, cross-check)
     bool fuse_divergence = true;  // F2D_FUSE_DIVERGENCE=0: separate divergence kernel (A/B, cross-check)
     std::vector<void*> registered;  // host ranges this solver page-locked (cudaHostRegister)
 
@@ -189,8 +190,11 @@ struct f2d_solver {
     // K relaxation sweeps for n problems.  in[i] == nullptr means a zero start (pressure).
     // out[i] receives the buffer holding the final iterate: a pool buffer the caller must
     // release, or in[i] itself when K == 0.
+    // With `src` != nullptr (diffuse, stream mode, K > 0) the first pass fuses add_sources: it reads the
+    // field in[i] and its source src[i], forms x0 = FMA(dt, s, f), WRITES it to rhs[i] (a pool buffer of
+    // the caller) and relaxes from it; the later passes read rhs[i] like any other right-hand side.
     int relax(int n, const float* const* in, const float* const* rhs, const int* kinds, const DiffuseCoef* coefs,
-              bool diffuse, uint32_t K, const float** out) {
+              bool diffuse, uint32_t K, const float** out, const float* const* src = nullptr, float src_dt = 0.f) {
         const float* cur[kMaxBatch];
         float* ping[kMaxBatch] = {nullptr, nullptr, nullptr};
         float* pong[kMaxBatch] = {nullptr, nullptr, nullptr};
@@ -221,11 +225,12 @@ struct f2d_solver {
             const float* todo[2 * kMaxBatch];
             int m = 0;
             for (int i = 0; i < n; ++i) {
-                if (get_inv(rhs[i]) > 0) todo[m++] = rhs[i];
-                if (cur[i] && cur[i] != rhs[i] && get_inv(cur[i]) > 0) todo[m++] = cur[i];
+                if (!src && get_inv(rhs[i]) > 0) todo[m++] = rhs[i];
+                if (cur[i] && (src || cur[i] != rhs[i]) && get_inv(cur[i]) > 0) todo[m++] = cur[i];
             }
             if (m) F2D_TRY(exchange(todo, m));
         }
+        bool fuse_src = (src != nullptr);
         while (left > 0) {
             uint32_t T = 1;
             if (stream_mode) {
@@ -239,7 +244,7 @@ struct f2d_solver {
                 int m = 0;
                 for (int i = 0; i < n; ++i) {
                     const bool xp = cur[i] && get_inv(cur[i]) + (int)T > H();
-                    const bool xr = get_inv(rhs[i]) + (int)T - 1 > H();
+                    const bool xr = !fuse_src && get_inv(rhs[i]) + (int)T - 1 > H();
                     if (xp) todo[m++] = cur[i];
                     if (xr && !(xp && rhs[i] == cur[i])) todo[m++] = rhs[i];
                 }
@@ -247,11 +252,12 @@ struct f2d_solver {
             }
             RelaxBatch b;
             b.n = n;
+            b.dt = src_dt;
             for (int i = 0; i < n; ++i) {
                 b.f[i].prev = cur[i];
-                b.f[i].rhs = rhs[i];
+                b.f[i].rhs = fuse_src ? src[i] : rhs[i];
                 b.f[i].next = flip ? pong[i] : ping[i];
-                b.f[i].aux = nullptr;
+                b.f[i].aux = fuse_src ? const_cast<float*>(rhs[i]) : nullptr;
                 b.f[i].kind = kinds[i];
                 b.f[i].coef = coefs ? coefs[i] : DiffuseCoef{0.f, 0.f, 0.f, 0.f, 1.0};
             }
@@ -262,9 +268,11 @@ struct f2d_solver {
             count();
             for (int i = 0; i < n; ++i) {
                 const int ip = cur[i] ? get_inv(cur[i]) : 0;
+                if (fuse_src) set_inv(rhs[i], ip);  // x0 is pointwise in the field
                 set_inv(b.f[i].next, std::max(ip + (int)T, get_inv(rhs[i]) + (int)T - 1));
                 cur[i] = b.f[i].next;
             }
+            fuse_src = false;
             flip ^= 1;
             left -= T;
         }
@@ -300,6 +308,7 @@ struct f2d_solver {
             if (!p1) return fail(F2D_ERR_STATE, "scratch pool exhausted");
             RelaxBatch b;
             b.n = 1;
+            b.dt = 0.f;
             b.f[0].prev = u_in;
             b.f[0].rhs = v_in;
             b.f[0].next = p1;
@@ -345,36 +354,40 @@ struct f2d_solver {
             set_inv(v, H());
             if (cfl_cells + 1 > H()) return fail(F2D_ERR_INVALID, "halo (%d) shallower than the advection radius (%d)", H(), cfl_cells + 1);
         }
-        // ---- add_sources for all three fields in one launch (gpu.cu:237, :243-244).  u and v get
-        //      their sources OUT of place: the density scatter below still needs the pre-step u, v
-        //      (the reference runs the whole density chain first, gpu.cu:236-240).
-        float *us = acquire(), *vs = acquire();
-        if (!us || !vs) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-        {
-            AddSourceBatch ab;
-            ab.n = 3;
-            ab.f[0] = d;
-            ab.o[0] = d;
-            ab.s[0] = state[F2D_FIELD_DENSITY_SOURCE];
-            ab.f[1] = u;
-            ab.o[1] = us;
-            ab.s[1] = state[F2D_FIELD_U_SOURCE];
-            ab.f[2] = v;
-            ab.o[2] = vs;
-            ab.s[2] = state[F2D_FIELD_V_SOURCE];
-            launch_add_sources(g, ab, dt, stream);
-            count();
-            set_inv(us, get_inv(u));  // pointwise: halo validity carries over
-            set_inv(vs, get_inv(v));
-        }
-        // ---- diffuse d, u, v in one batch (gpu.cu:238, :245-246): x0 == the field after add_sources
+        // ---- add_sources + diffuse for d, u, v (gpu.cu:237-238, :243-246).  u and v get their sources OUT of
+        //      place: the density scatter below still needs the pre-step u, v (the reference runs the whole
+        //      density chain first, gpu.cu:236-240).  In stream mode add_sources is fused into the first
+        //      diffuse pass, which writes x0 (the field after add_sources == the rhs of the relaxation).
+        const bool fuse_src = fuse_sources && cfg.jacobi_mode == F2D_JACOBI_STREAM && cfg.diffuse_iters > 0;
+        float *ds = fuse_src ? acquire() : d, *us = acquire(), *vs = acquire();
+        if (!ds || !us || !vs) return fail(F2D_ERR_STATE, "scratch pool exhausted");
         const float* dif[3];
         {
-            const float* in[3] = {d, us, vs};
-            const float* rhs[3] = {d, us, vs};
             const int kind[3] = {F2D_BND_CONTINUOUS, F2D_BND_OPPOSITE_HORIZONTAL, F2D_BND_OPPOSITE_VERTICAL};
             const DiffuseCoef kc[3] = {diffuse_coef(diffusion_rate, dt), diffuse_coef(viscosity, dt), diffuse_coef(viscosity, dt)};
-            F2D_TRY(relax(3, in, rhs, kind, kc, true, cfg.diffuse_iters, dif));
+            const float* x0[3] = {ds, us, vs};
+            if (fuse_src) {
+                const float* in[3] = {d, u, v};
+                const float* srcs[3] = {state[F2D_FIELD_DENSITY_SOURCE], state[F2D_FIELD_U_SOURCE], state[F2D_FIELD_V_SOURCE]};
+                F2D_TRY(relax(3, in, x0, kind, kc, true, cfg.diffuse_iters, dif, srcs, dt));
+            } else {
+                AddSourceBatch ab;
+                ab.n = 3;
+                ab.f[0] = d;
+                ab.o[0] = d;
+                ab.s[0] = state[F2D_FIELD_DENSITY_SOURCE];
+                ab.f[1] = u;
+                ab.o[1] = us;
+                ab.s[1] = state[F2D_FIELD_U_SOURCE];
+                ab.f[2] = v;
+                ab.o[2] = vs;
+                ab.s[2] = state[F2D_FIELD_V_SOURCE];
+                launch_add_sources(g, ab, dt, stream);
+                count();
+                set_inv(us, get_inv(u));  // pointwise: halo validity carries over
+                set_inv(vs, get_inv(v));
+                F2D_TRY(relax(3, x0, x0, kind, kc, true, cfg.diffuse_iters, dif));  // x0 == the field after add_sources
+            }
         }
         // ---- density: forward scatter by the PRE-step (u, v), boundary pass + smooth (gpu.cu:239-240)
         {
@@ -384,6 +397,7 @@ struct f2d_solver {
             launch_scatter_density(g, dif[0], u, v, sc, dt0(dt), own_begin(), own_end(), oob_flag, stream);
             count();
             if (dif[0] != d) release(dif[0]);
+            if (ds != d) release(ds);
             if (multi()) {
                 // splats that landed in halo rows belong to the neighbour slab: send them home and add,
                 // then refresh the halos for the radius-1 smooth
@@ -789,6 +803,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     s->tune.rhs_in_smem = env_int("F2D_STREAM_RHS_SMEM", 0);
     s->tune.min_blocks = env_int("F2D_STREAM_MIN_BLOCKS", 0);
     s->fuse_divergence = env_int("F2D_FUSE_DIVERGENCE", 1) != 0;
+    s->fuse_sources = env_int("F2D_FUSE_SOURCES", 1) != 0;
 
     auto cleanup = [&](int rc) {
         f2d_destroy(s);
