@@ -377,7 +377,59 @@ __global__ void __launch_bounds__(kBx* kBy) k_smooth_bnd(Geom g, const float* __
                            bnd_read(g, in, i - 1, j), bnd_read(g, in, i + 1, j));
 }
 
+// float4 version (cols % 4 == 0).  B(in) at the neighbours of an interior row: the row above row 1 / below
+// row N-2 and the column left of column 1 / right of column N-2 are edge cells whose boundary value is the
+// interior cell itself.
+template <bool SMOOTH>
+__global__ void __launch_bounds__(kVx* kVy) k_smooth_bnd_v4(Geom g, const float* __restrict__ in, float* __restrict__ out) {
+    F2D_ROW_J4();
+    const int gi = g.grow0 + i;
+    const size_t o = (size_t)i * g.pitch + j;
+    const bool top = (gi == 0), bottom = (gi == g.grows - 1);
+    const bool first = (j == 0), last = (j + 3 == g.cols - 1);
+    if ((i == 0 && !top) || (i == g.rows - 1 && !bottom)) {  // slab-local edge row: pass through
+        st4(out + o, ld4(in + o));
+        return;
+    }
+    if (top || bottom) {  // global edge row: copy of the adjacent interior row, corners keep their value
+        const float4 here = ld4(in + o);
+        float4 r = ld4(in + (top ? o + g.pitch : o - g.pitch));
+        if (first) r.x = here.x;
+        if (last) r.w = here.w;
+        st4(out + o, r);
+        return;
+    }
+    const float4 c = ld4(in + o);
+    float4 r = c;
+    if (SMOOTH) {
+        const bool n_edge = (gi - 1 == 0), s_edge = (gi + 1 == g.grows - 1);
+        const bool can = (i >= 1 && i <= g.rows - 2);  // neighbours exist locally (always true for global interior rows of a full grid)
+        if (can) {
+            const float4 n = n_edge ? c : ld4(in + o - g.pitch);
+            const float4 sN = s_edge ? c : ld4(in + o + g.pitch);
+            const float wl = first ? 0.f : __ldg(in + o - 1);
+            const float er = last ? 0.f : __ldg(in + o + 4);
+            // B(in)(i, 0) == in(i, 1) and B(in)(i, N-1) == in(i, N-2)
+            r.x = smooth_update(c.x, wl, c.y, n.x, sN.x);
+            r.y = smooth_update(c.y, first ? c.y : c.x, c.z, n.y, sN.y);
+            r.z = smooth_update(c.z, c.y, last ? c.z : c.w, n.z, sN.z);
+            r.w = smooth_update(c.w, c.z, er, n.w, sN.w);
+        }
+    }
+    // edge columns of an interior row: boundary value = the neighbouring interior cell of the INPUT
+    if (first) r.x = c.y;
+    if (last) r.w = c.z;
+    st4(out + o, r);
+}
+
 void launch_smooth_bnd(const Geom& g, const float* in, float* out, bool do_smooth, cudaStream_t st) {
+    if (g.cols % 4 == 0 && g.cols >= 8) {
+        if (do_smooth)
+            k_smooth_bnd_v4<true><<<grid_v4(g), dim3(kVx, kVy), 0, st>>>(g, in, out);
+        else
+            k_smooth_bnd_v4<false><<<grid_v4(g), dim3(kVx, kVy), 0, st>>>(g, in, out);
+        return;
+    }
     if (do_smooth)
         k_smooth_bnd<true><<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, in, out);
     else
