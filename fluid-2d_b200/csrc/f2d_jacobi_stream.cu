@@ -444,10 +444,10 @@ struct ClassPlan {
     int chunks, chunk_rows, trim;
 };
 
-inline ClassPlan plan_class(int rows, int T, int RS, double cost_budget, double c_class, bool both_edges) {
+inline ClassPlan plan_class(int rows, int T, int RS, double cost_budget, double c_class, bool both_edges, int min_mult) {
     ClassPlan cp;
     int ch = (int)(cost_budget / c_class) - 2 * T;  // rows per chunk at this budget
-    ch = std::max(ch, 4 * T);
+    ch = std::max(ch, min_mult * T);  // bound the warm-up redundancy on small grids
     ch = std::min(ch, rows);
     int trim = both_edges ? (int)((T + RS / 2) * (kCheckedStepCost - 1.0)) : 0;
     if (ch < 2 * trim + 2 || ch >= rows) trim = 0;
@@ -485,6 +485,7 @@ void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, in
     const int n_int = plan.strips - plan.n_edge_strips;
     const bool both_edges = (g.grow0 == 0 && g.grow0 + g.rows == g.grows);
     const long slots = (long)occ_cache[wpc] * sm_count * wpc / b.n;  // warps available per field
+    const int min_mult = tune.min_chunk_mult > 0 ? tune.min_chunk_mult : 2;  // profiles/tune_small_r01.log
     ClassPlan ci = {0, 0, 0}, ce = {0, 0, 0};
     if (tune.chunk_rows > 0) {  // manual override: same height for both classes, no trimming
         ci.chunk_rows = ce.chunk_rows = std::min(tune.chunk_rows, g.rows);
@@ -494,16 +495,16 @@ void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, in
         double lo = 4.0 * T, hi = (double)(g.rows + 2 * T) * kEdgeStripCost + 1.0;
         for (int it = 0; it < 40; ++it) {
             const double mid = 0.5 * (lo + hi);
-            const ClassPlan a = plan_class(g.rows, T, RS, mid, 1.0, both_edges);
-            const ClassPlan e = plan_class(g.rows, T, RS, mid, kEdgeStripCost, both_edges);
+            const ClassPlan a = plan_class(g.rows, T, RS, mid, 1.0, both_edges, min_mult);
+            const ClassPlan e = plan_class(g.rows, T, RS, mid, kEdgeStripCost, both_edges, min_mult);
             const long warps = (long)n_int * a.chunks + (long)plan.n_edge_strips * e.chunks;
             if (warps <= slots)
                 hi = mid;
             else
                 lo = mid;
         }
-        ci = plan_class(g.rows, T, RS, hi, 1.0, both_edges);
-        ce = plan_class(g.rows, T, RS, hi, kEdgeStripCost, both_edges);
+        ci = plan_class(g.rows, T, RS, hi, 1.0, both_edges, min_mult);
+        ce = plan_class(g.rows, T, RS, hi, kEdgeStripCost, both_edges, min_mult);
     }
     plan.chunks[0] = ci.chunks;
     plan.chunk_rows[0] = ci.chunk_rows;

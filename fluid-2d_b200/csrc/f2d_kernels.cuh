@@ -59,6 +59,7 @@ struct StreamTuning {
     int warps_per_cta;  // 0 = auto
     int rhs_in_smem;    // 0 = rhs rows ride in a register ring (default), 1 = re-read from the smem ring
     int min_blocks;     // 0 = default register budget; see launch_jacobi_stream
+    int min_chunk_mult; // chunks own at least min_chunk_mult * T rows (0 = 2)
 };
 // `sweeps` (1..T) Jacobi sweeps in one pass over the field(s); returns false if (T, geometry)
 // is not supported by the streaming kernel.

@@ -84,7 +84,7 @@ struct f2d_solver {
     GraphKey graph_key = {0.f, 0.f, 0.f, false};
     uint64_t graph_kernels = 0;  // kernel launches inside one replay of the graph
     uint64_t launches = 0;       // kernel launches issued so far (graph nodes included)
-    StreamTuning tune = {0, 0, 0, 0};
+    StreamTuning tune = {0, 0, 0, 0, 0};
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // solve(): the density field is final long before the velocity projections finish; it is copied
@@ -785,10 +785,13 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
 
     // sweeps fused per pass: 8 is fastest for both relaxations at 4096^2 and 16384^2
     // (profiles/tune_r01_run5_*.jsonl); the two can be set independently
+    // grids up to ~1024^2 are launch/latency bound: shallower pipelines (less warm-up per chunk) win there
+    // (profiles/tune_small_r01.log: 1024^2 K=40 0.304 ms at T=4 vs 0.342 at T=8; 256^2 K=20 0.107 vs 0.129)
+    const int auto_T = ((uint64_t)grows * cfg->cols <= 1200ull * 1200ull) ? 4 : 8;
     if (s->cfg.temporal_block_diffuse == 0)
         s->cfg.temporal_block_diffuse =
-            s->cfg.temporal_block ? s->cfg.temporal_block : (uint32_t)env_int("F2D_TEMPORAL_BLOCK_DIFFUSE", env_int("F2D_TEMPORAL_BLOCK", 8));
-    if (s->cfg.temporal_block == 0) s->cfg.temporal_block = (uint32_t)env_int("F2D_TEMPORAL_BLOCK", 8);
+            s->cfg.temporal_block ? s->cfg.temporal_block : (uint32_t)env_int("F2D_TEMPORAL_BLOCK_DIFFUSE", env_int("F2D_TEMPORAL_BLOCK", auto_T));
+    if (s->cfg.temporal_block == 0) s->cfg.temporal_block = (uint32_t)env_int("F2D_TEMPORAL_BLOCK", auto_T);
     if (s->cfg.jacobi_mode == F2D_JACOBI_STREAM) {
         if (!stream_supported(s->g, (int)s->cfg.temporal_block) || !stream_supported(s->g, (int)s->cfg.temporal_block_diffuse)) {
             delete s;
@@ -802,6 +805,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     s->tune.warps_per_cta = env_int("F2D_STREAM_WARPS_PER_CTA", 0);
     s->tune.rhs_in_smem = env_int("F2D_STREAM_RHS_SMEM", 0);
     s->tune.min_blocks = env_int("F2D_STREAM_MIN_BLOCKS", 0);
+    s->tune.min_chunk_mult = env_int("F2D_STREAM_MIN_CHUNK_MULT", 0);
     s->fuse_divergence = env_int("F2D_FUSE_DIVERGENCE", 1) != 0;
     s->fuse_sources = env_int("F2D_FUSE_SOURCES", 1) != 0;
 

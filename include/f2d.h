@@ -76,7 +76,7 @@ typedef struct f2d_config {
     uint32_t project_iters;  /* Kp; fluid_solver_gpu::solve uses 20 (gpu.cu:247,252)            */
     uint32_t smooth;         /* 1 = density smooth after advect as gpu.cu:240 (default)         */
     uint32_t jacobi_mode;    /* F2D_JACOBI_*                                                    */
-    uint32_t temporal_block; /* sweeps fused per pass of the PRESSURE solve (1,2,4,8); 0 = auto (8) */
+    uint32_t temporal_block; /* sweeps fused per pass of the PRESSURE solve (1,2,4,8); 0 = auto (4 up to ~1024^2, else 8) */
     uint32_t divide_mode;    /* F2D_DIV_*                                                       */
     uint32_t use_graph;      /* 1 = capture the step into a CUDA graph (default)                */
     int32_t device;          /* CUDA device ordinal; -1 = current device                        */
@@ -86,7 +86,7 @@ typedef struct f2d_config {
     uint32_t global_rows;
     uint32_t row_offset;
     uint32_t halo;
-    uint32_t temporal_block_diffuse; /* same for the diffuse solve; 0 = auto (temporal_block if set, else 8) */
+    uint32_t temporal_block_diffuse; /* same for the diffuse solve; 0 = auto (temporal_block if set, else as above) */
     void* stream; /* cudaStream_t to run on; NULL = the solver creates its own                  */
 } f2d_config;
 
