@@ -49,8 +49,11 @@ def run_multi_gpu(args, workload):
     halo = int(os.environ.get("F2D_HALO", "32"))
     cfl = 8
     sl = slabmod.partition(n, world, halo, rank)
-    uid = slabmod.broadcast_unique_id(dist, rank, device=torch.device("cuda", local_rank))
-    solver = slabmod.make_slab_solver(sl, n, uid, cfl_cells=cfl, device=local_rank, diffuse_iters=kd, project_iters=kp)
+    transport = os.environ.get("F2D_TRANSPORT", "p2p")
+    tdev = torch.device("cuda", local_rank)
+    uid = slabmod.broadcast_unique_id(dist, rank, device=tdev) if transport == "nccl" else None
+    solver = slabmod.make_slab_solver(sl, n, uid, cfl_cells=cfl, device=local_rank, transport=transport, dist=dist,
+                                      torch_device=tdev, diffuse_iters=kd, project_iters=kp)
     cfg = solver.config()
     d, u, v, sd, su, sv = canonical_rows(n, sl.row_offset, sl.row_offset + sl.rows)
     solver.upload(d, u, v)
@@ -108,7 +111,8 @@ def run_multi_gpu(args, workload):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": workload["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload["name"], "grid": [n, n], "diffuse_iters": kd, "project_iters": kp,
-                       "parallelism": "row slabs x%d, halo %d rows, NCCL send/recv in the step graph" % (world, halo),
+                       "parallelism": "row slabs x%d, halo %d rows, %s" % (world, halo, "direct NVLink peer stores + epoch-flag handshake in the step graph" if transport == "p2p" else "NCCL send/recv in the step graph"),
+                       "transport": transport,
                        "temporal_block": int(cfg.temporal_block), "temporal_block_diffuse": int(cfg.temporal_block_diffuse), "jacobi_mode": int(cfg.jacobi_mode),
                        "divide_mode": int(cfg.divide_mode), "cfl_cells": cfl,
                        "l2": "inputs larger than L2 (slab fields of %.0f MiB)" % (sl.rows * n * 4 / 2**20)},

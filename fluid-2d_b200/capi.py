@@ -115,6 +115,9 @@ def load():
         "f2d_comm_unique_id": [C.c_char_p],
         "f2d_comm_init": [vp, C.c_char_p, i32, i32, i32],
         "f2d_comm_stats": [vp, C.POINTER(C.c_uint64)],
+        "f2d_p2p_export": [vp, C.POINTER(C.c_ubyte), C.POINTER(C.c_uint64)],
+        "f2d_p2p_connect": [vp, i32, i32, C.POINTER(C.c_ubyte), C.POINTER(C.c_uint64), C.POINTER(C.c_ubyte),
+                            C.POINTER(C.c_uint64), i32],
         "f2d_render_density_rgba": [vp, f32, f32, f32, C.POINTER(C.c_ubyte)],
         "f2d_render_velocity_lines": [vp, f32, f32, fp],
         "f2d_abi_version": [],

@@ -48,6 +48,21 @@ void launch_smooth_bnd(const Geom& g, const float* in, float* out, bool do_smoot
 void launch_smooth_plain(const Geom& g, const float* in, float* out, cudaStream_t st);
 void launch_set_bnd_inplace(const Geom& g, float* f, int kind, cudaStream_t st);
 
+// ---- peer-to-peer halo exchange (f2d_p2p.cu)
+struct XchgSeg {
+    const float4* src;  // my rows
+    float4* dst;        // the neighbour's rows (peer-mapped)
+    unsigned n4;        // float4 count
+};
+struct XchgParams {
+    XchgSeg seg[8];
+    int nseg;
+    unsigned* my_flags;    // this rank's flag block
+    unsigned* up_flags;    // the neighbours' flag blocks (peer-mapped), nullptr at the global edges
+    unsigned* down_flags;
+};
+void launch_halo_xchg(const XchgParams& p, cudaStream_t st);
+
 // ---- headless renderers (f2d_render.cu)
 void launch_density_to_rgba(const Geom& g, const float* d, void* img, float mr, float mg, float mb, cudaStream_t st);
 void launch_velocity_to_lines(const Geom& g, const float* u, const float* v, void* lines, float hscale, float vscale,

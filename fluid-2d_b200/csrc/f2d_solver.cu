@@ -150,10 +150,27 @@ struct f2d_solver {
     int rank = 0, nranks = 1;
     int cfl_cells = 8;     // bound on the advection displacement per step, in cells (caller's promise)
     float *rx_up = nullptr, *rx_down = nullptr;  // landing zones of the reverse (scatter) exchange
+    char* arena = nullptr;                       // the single device allocation all of the above live in
+    size_t arena_bytes = 0, field_stride = 0, rx_bytes = 0;
+    unsigned* flags = nullptr;                   // P2P transport: epoch + handshake flags (see f2d_p2p.cu)
+    struct PeerLink {                            // a neighbour's arena opened through CUDA IPC
+        char* arena = nullptr;
+        size_t field_stride = 0, rx_bytes = 0;
+        int rows = 0, nbuf = 0;
+        unsigned* flags() const { return reinterpret_cast<unsigned*>(arena + (size_t)nbuf * field_stride + 2 * rx_bytes); }
+        float* rx_up() const { return reinterpret_cast<float*>(arena + (size_t)nbuf * field_stride); }
+        float* rx_down() const { return reinterpret_cast<float*>(arena + (size_t)nbuf * field_stride + rx_bytes); }
+    };
+    PeerLink peer_up, peer_down;
+    bool p2p = false;                            // halo transport: direct peer stores (true) or NCCL (comm != nullptr)
+    int nbuffers() const { return 6 + (int)temps.size(); }
+    int buffer_index(const float* p) const { return (int)((reinterpret_cast<const char*>(p) - arena) / (ptrdiff_t)field_stride); }
+    int exchange_p2p(const float* const* bufs, int n);
+    int reverse_exchange_p2p(float* buf);
     uint64_t exchanges = 0, exchanges_in_graph = 0;
     std::vector<std::pair<const float*, int>> inv_table;
 
-    bool multi() const { return comm != nullptr; }
+    bool multi() const { return comm != nullptr || p2p; }
     int H() const { return (int)cfg.halo; }
     bool has_up() const { return g.grow0 > 0; }
     bool has_down() const { return g.grow0 + g.rows < g.grows; }
@@ -598,6 +615,7 @@ int load_nccl() {
 // into mine.  All listed buffers travel in one NCCL group (one fused P2P kernel over NVLink).
 int f2d_solver::exchange(const float* const* bufs, int n) {
     if (!multi() || n == 0) return F2D_OK;
+    if (p2p) return exchange_p2p(bufs, n);
     const size_t cnt = (size_t)H() * (size_t)g.pitch;
     F2D_NCCL(g_nccl.GroupStart());
     for (int i = 0; i < n; ++i) {
@@ -622,6 +640,7 @@ int f2d_solver::exchange(const float* const* bufs, int n) {
 // the neighbour; they are sent home and added to its first/last owned rows.
 int f2d_solver::reverse_exchange_add(float* buf) {
     if (!multi()) return F2D_OK;
+    if (p2p) return reverse_exchange_p2p(buf);
     const size_t cnt = (size_t)H() * (size_t)g.pitch;
     F2D_NCCL(g_nccl.GroupStart());
     if (has_up()) {
@@ -647,8 +666,128 @@ int f2d_solver::reverse_exchange_add(float* buf) {
     return F2D_OK;
 }
 
+// ------------------------------------------------------------- peer-to-peer transport (f2d_p2p.cu)
+int f2d_solver::exchange_p2p(const float* const* bufs, int n) {
+    const unsigned n4 = (unsigned)((size_t)H() * g.pitch / 4);
+    const size_t halo_floats = (size_t)H() * g.pitch;
+    XchgParams P;
+    P.my_flags = flags;
+    P.up_flags = has_up() ? peer_up.flags() : nullptr;
+    P.down_flags = has_down() ? peer_down.flags() : nullptr;
+    P.nseg = 0;
+    for (int i = 0; i < n; ++i) {
+        const float* b = bufs[i];
+        const int idx = buffer_index(b);
+        if (idx < 0 || idx >= nbuffers()) return fail(F2D_ERR_STATE, "exchange of a buffer outside the arena");
+        if (has_up()) {  // my rows [H, 2H) -> the upper neighbour's bottom halo rows [rows_up - H, rows_up)
+            float* dst = reinterpret_cast<float*>(peer_up.arena + (size_t)idx * peer_up.field_stride) +
+                         (size_t)(peer_up.rows - H()) * g.pitch;
+            P.seg[P.nseg++] = {reinterpret_cast<const float4*>(b + halo_floats), reinterpret_cast<float4*>(dst), n4};
+        }
+        if (has_down()) {  // my rows [rows - 2H, rows - H) -> the lower neighbour's top halo rows [0, H)
+            float* dst = reinterpret_cast<float*>(peer_down.arena + (size_t)idx * peer_down.field_stride);
+            P.seg[P.nseg++] = {reinterpret_cast<const float4*>(b + (size_t)(g.rows - 2 * H()) * g.pitch),
+                               reinterpret_cast<float4*>(dst), n4};
+        }
+        if ((i + 1) % 4 == 0 || i == n - 1) {  // <= 4 buffers (8 segments) per kernel; chunking by BUFFER count so that
+                                                // every rank (edge ranks have one neighbour) issues the same handshakes
+            launch_halo_xchg(P, stream);
+            count();
+            ++exchanges;
+            P.nseg = 0;
+        }
+    }
+    F2D_CUDA(cudaGetLastError());
+    for (int i = 0; i < n; ++i) set_inv(bufs[i], 0);
+    return F2D_OK;
+}
+
+int f2d_solver::reverse_exchange_p2p(float* buf) {
+    const unsigned n4 = (unsigned)((size_t)H() * g.pitch / 4);
+    XchgParams P;
+    P.my_flags = flags;
+    P.up_flags = has_up() ? peer_up.flags() : nullptr;
+    P.down_flags = has_down() ? peer_down.flags() : nullptr;
+    P.nseg = 0;
+    // the partial sums in my halo rows go to the owner's landing zone: my top halo is the upper neighbour's
+    // "from below" zone (rx_down there), my bottom halo the lower neighbour's "from above" zone (rx_up)
+    if (has_up()) P.seg[P.nseg++] = {reinterpret_cast<const float4*>(buf), reinterpret_cast<float4*>(peer_up.rx_down()), n4};
+    if (has_down())
+        P.seg[P.nseg++] = {reinterpret_cast<const float4*>(buf + (size_t)(g.rows - H()) * g.pitch),
+                           reinterpret_cast<float4*>(peer_down.rx_up()), n4};
+    launch_halo_xchg(P, stream);
+    count();
+    if (has_up()) {
+        launch_add_rows(g, buf, H(), H(), rx_up, stream);
+        count();
+    }
+    if (has_down()) {
+        launch_add_rows(g, buf, g.rows - 2 * H(), H(), rx_down, stream);
+        count();
+    }
+    F2D_CUDA(cudaGetLastError());
+    ++exchanges;
+    set_inv(buf, H());
+    return F2D_OK;
+}
+
 // =============================================================================== C ABI
 extern "C" {
+
+// ---- multi-GPU over peer memory: every rank exports one IPC handle for its arena; the host side gathers
+// them (torch.distributed) and hands each rank its neighbours' handles.
+F2D_API int f2d_p2p_export(f2d_solver* s, unsigned char* handle64, uint64_t* info4) {
+    if (!s || !handle64 || !info4) return fail(F2D_ERR_INVALID, "NULL argument");
+    F2D_CUDA(cudaSetDevice(s->device));
+    cudaIpcMemHandle_t h;
+    F2D_CUDA(cudaIpcGetMemHandle(&h, s->arena));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    info4[0] = s->field_stride;
+    info4[1] = (uint64_t)s->g.rows;
+    info4[2] = s->rx_bytes;
+    info4[3] = (uint64_t)s->nbuffers();
+    return F2D_OK;
+}
+
+F2D_API int f2d_p2p_connect(f2d_solver* s, int rank, int nranks, const unsigned char* up_handle64, const uint64_t* up_info4,
+                            const unsigned char* down_handle64, const uint64_t* down_info4, int cfl_cells) {
+    if (!s) return fail(F2D_ERR_INVALID, "NULL argument");
+    if (nranks < 2 || rank < 0 || rank >= nranks) return fail(F2D_ERR_INVALID, "bad rank/nranks");
+    if (s->cfg.halo == 0) return fail(F2D_ERR_INVALID, "a slab solver needs halo > 0");
+    if (s->multi()) return fail(F2D_ERR_STATE, "communicator already initialised");
+    if ((s->g.grow0 > 0) != (rank > 0) || (s->g.grow0 + s->g.rows < s->g.grows) != (rank < nranks - 1))
+        return fail(F2D_ERR_INVALID, "slab position does not match rank (slabs are ordered by rank)");
+    if (s->g.rows < 3 * (int)s->cfg.halo) return fail(F2D_ERR_INVALID, "slab thinner than 3 halos");
+    if ((s->has_up() && (!up_handle64 || !up_info4)) || (s->has_down() && (!down_handle64 || !down_info4)))
+        return fail(F2D_ERR_INVALID, "missing neighbour handle");
+    F2D_CUDA(cudaSetDevice(s->device));
+    auto open = [&](f2d_solver::PeerLink& L, const unsigned char* h64, const uint64_t* info) -> int {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, h64, 64);
+        void* p = nullptr;
+        F2D_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        L.arena = static_cast<char*>(p);
+        L.field_stride = (size_t)info[0];
+        L.rows = (int)info[1];
+        L.rx_bytes = (size_t)info[2];
+        L.nbuf = (int)info[3];
+        if (L.nbuf != s->nbuffers() || L.rx_bytes != s->rx_bytes) return fail(F2D_ERR_INVALID, "neighbour solver has a different configuration");
+        return F2D_OK;
+    };
+    if (s->has_up()) F2D_TRY(open(s->peer_up, up_handle64, up_info4));
+    if (s->has_down()) F2D_TRY(open(s->peer_down, down_handle64, down_info4));
+    s->p2p = true;
+    s->rank = rank;
+    s->nranks = nranks;
+    s->cfl_cells = cfl_cells > 0 ? cfl_cells : 8;
+    if (s->graph_exec) {
+        cudaGraphExecDestroy(s->graph_exec);
+        s->graph_exec = nullptr;
+        s->graph_key.valid = false;
+    }
+    return F2D_OK;
+}
 
 // ---- multi-GPU bootstrap: rank 0 makes the id, the host side broadcasts it (torch.distributed),
 // every rank calls f2d_comm_init (collective).
@@ -675,9 +814,6 @@ F2D_API int f2d_comm_init(f2d_solver* s, const char* id128, int rank, int nranks
     memcpy(id.internal, id128, sizeof(id.internal));
     void* comm = nullptr;
     F2D_NCCL(g_nccl.CommInitRank(&comm, nranks, id, rank));
-    const size_t bytes = (size_t)s->cfg.halo * s->g.pitch * sizeof(float);
-    F2D_CUDA(cudaMalloc(&s->rx_up, bytes));
-    F2D_CUDA(cudaMalloc(&s->rx_down, bytes));
     s->comm = comm;
     s->rank = rank;
     s->nranks = nranks;
@@ -820,20 +956,24 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
             return cleanup(fail(F2D_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
         s->own_stream = true;
     }
-    for (int i = 0; i < 6; ++i) {
-        if (cudaMalloc(&s->state[i], s->field_bytes) != cudaSuccess)
-            return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc(%zu) failed: %s", s->field_bytes, cudaGetErrorString(cudaGetLastError())));
-        cudaMemsetAsync(s->state[i], 0, s->field_bytes, s->stream);
-    }
-    const int ntemps = 11;  // deepest point: batched diffuse (2 add_sources outputs + 3x2 ping-pong + p/div views)
+    // One arena for everything peers may touch: 6 state fields, the scratch pool, the two landing zones of
+    // the reverse (scatter) exchange and a flag block.  One allocation == one CUDA IPC handle per rank, and a
+    // buffer is identified across ranks by its index (every rank runs the same schedule on the same pool).
+    const int ntemps = 11;  // deepest point: batched diffuse (3 x0 + 3x2 ping-pong + p/div views)
+    s->field_stride = (s->field_bytes + 511) / 512 * 512;
+    s->rx_bytes = ((size_t)cfg->halo * s->g.pitch * sizeof(float) + 511) / 512 * 512;
+    s->arena_bytes = (size_t)(6 + ntemps) * s->field_stride + 2 * s->rx_bytes + 4096;
+    if (cudaMalloc(&s->arena, s->arena_bytes) != cudaSuccess)
+        return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc(%zu) failed: %s", s->arena_bytes, cudaGetErrorString(cudaGetLastError())));
+    cudaMemsetAsync(s->arena, 0, s->arena_bytes, s->stream);
+    for (int i = 0; i < 6; ++i) s->state[i] = reinterpret_cast<float*>(s->arena + (size_t)i * s->field_stride);
     for (int i = 0; i < ntemps; ++i) {
-        float* p = nullptr;
-        if (cudaMalloc(&p, s->field_bytes) != cudaSuccess)
-            return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc(%zu) failed: %s", s->field_bytes, cudaGetErrorString(cudaGetLastError())));
-        cudaMemsetAsync(p, 0, s->field_bytes, s->stream);
-        s->temps.push_back(p);
+        s->temps.push_back(reinterpret_cast<float*>(s->arena + (size_t)(6 + i) * s->field_stride));
         s->temp_busy.push_back(0);
     }
+    s->rx_up = reinterpret_cast<float*>(s->arena + (size_t)(6 + ntemps) * s->field_stride);
+    s->rx_down = reinterpret_cast<float*>(s->arena + (size_t)(6 + ntemps) * s->field_stride + s->rx_bytes);
+    s->flags = reinterpret_cast<unsigned*>(s->arena + (size_t)(6 + ntemps) * s->field_stride + 2 * s->rx_bytes);
     if (cudaMalloc(&s->oob_flag, sizeof(int)) != cudaSuccess)
         return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
     cudaMemsetAsync(s->oob_flag, 0, sizeof(int), s->stream);
@@ -856,13 +996,13 @@ F2D_API void f2d_destroy(f2d_solver* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     for (int i = 0; i < 6; ++i)
-        if (s->state[i]) cudaFree(s->state[i]);
-    for (float* p : s->temps) cudaFree(p);
+        s->state[i] = nullptr;
+    if (s->arena) cudaFree(s->arena);
     if (s->oob_flag) cudaFree(s->oob_flag);
     if (s->render_buf) cudaFree(s->render_buf);
-    if (s->rx_up) cudaFree(s->rx_up);
-    if (s->rx_down) cudaFree(s->rx_down);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    if (s->peer_up.arena) cudaIpcCloseMemHandle(s->peer_up.arena);
+    if (s->peer_down.arena) cudaIpcCloseMemHandle(s->peer_down.arena);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->copy_stream) {
@@ -957,6 +1097,11 @@ F2D_API int f2d_sync(f2d_solver* s) {
     F2D_CUDA(cudaStreamSynchronize(s->stream));
     int oob = 0;
     F2D_CUDA(cudaMemcpy(&oob, s->oob_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (s->p2p) {
+        unsigned err = 0;
+        F2D_CUDA(cudaMemcpy(&err, s->flags + 2, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (err) return fail(F2D_ERR_STATE, "halo exchange timed out waiting for a neighbour GPU");
+    }
     if (oob) {
         cudaMemset(s->oob_flag, 0, sizeof(int));
         return fail(F2D_ERR_STATE, "density scatter left the slab: displacement exceeded the halo (CFL bound violated)");

@@ -69,12 +69,50 @@ def broadcast_unique_id(dist, rank, device=None):
     return bytes(buf.cpu().numpy().tobytes())
 
 
-def make_slab_solver(slab, cols, unique_id, cfl_cells=8, device=0, **solver_kwargs):
-    """FluidSolverB200 for one slab, communicator initialised (collective over all ranks)."""
+def gather_p2p_handles(dist, solver, world, device=None):
+    """Every rank exports the CUDA IPC handle of its arena + 4 words of geometry (f2d_p2p_export);
+    torch.distributed all-gathers the 96-byte records.  Returns a list of (handle bytes, info array)."""
+    import torch
+
+    h = (C.c_ubyte * 64)()
+    info = (C.c_uint64 * 4)()
+    capi.check(capi.load().f2d_p2p_export(solver._h, h, info))
+    rec = torch.frombuffer(bytearray(bytes(h) + bytes(info)), dtype=torch.uint8).clone()
+    if device is not None:
+        rec = rec.to(device)
+    out = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(out, rec)
+    recs = []
+    for t in out:
+        b = t.cpu().numpy().tobytes()
+        recs.append((b[:64], np.frombuffer(b[64:96], dtype=np.uint64).copy()))
+    return recs
+
+
+def make_slab_solver(slab, cols, unique_id=None, cfl_cells=8, device=0, transport="nccl", dist=None, torch_device=None,
+                     **solver_kwargs):
+    """FluidSolverB200 for one slab with its halo transport wired (collective over all ranks).
+    transport="nccl": NCCL send/recv pairs (needs unique_id from broadcast_unique_id);
+    transport="p2p" : direct peer stores over NVLink (needs dist: handles are all-gathered here)."""
     s = FluidSolverB200(slab.rows, cols, global_rows=slab.global_rows, row_offset=slab.row_offset,
                         halo=slab.halo, device=device, **solver_kwargs)
     if slab.world > 1:
-        capi.check(capi.load().f2d_comm_init(s._h, unique_id, slab.rank, slab.world, cfl_cells))
+        L = capi.load()
+        if transport == "p2p":
+            recs = gather_p2p_handles(dist, s, slab.world, device=torch_device)
+
+            def arg(r):
+                if r < 0 or r >= slab.world:
+                    return None, None
+                hb, info = recs[r]
+                return (C.c_ubyte * 64).from_buffer_copy(hb), (C.c_uint64 * 4)(*[int(x) for x in info])
+
+            uh, ui = arg(slab.rank - 1)
+            dh, di = arg(slab.rank + 1)
+            capi.check(L.f2d_p2p_connect(s._h, slab.rank, slab.world, uh, ui, dh, di, cfl_cells))
+            dist.barrier()  # every rank has opened its neighbours' arenas before anyone steps
+        else:
+            capi.check(L.f2d_comm_init(s._h, unique_id, slab.rank, slab.world, cfl_cells))
     return s
 
 

@@ -160,6 +160,14 @@ F2D_API int f2d_launch_count(const f2d_solver* s, uint64_t* launches);
 F2D_API int f2d_comm_unique_id(char* id128);
 F2D_API int f2d_comm_init(f2d_solver* s, const char* id128, int rank, int nranks, int cfl_cells);
 F2D_API int f2d_comm_stats(const f2d_solver* s, uint64_t* exchanges);
+/* The same slabs with the halo transport replaced by direct NVLink peer stores (f2d_p2p.cu): one kernel
+ * per exchange pushes the rows into the neighbour's halo and handshakes through epoch flags in device
+ * memory; no NCCL call on the data path.  Every rank exports one 64-byte CUDA IPC handle of its arena plus
+ * four words of geometry; the host side gathers them and passes each rank its neighbours' (NULL at the
+ * global edges).  Use either f2d_comm_init or f2d_p2p_connect, not both. */
+F2D_API int f2d_p2p_export(f2d_solver* s, unsigned char* handle64, uint64_t* info4);
+F2D_API int f2d_p2p_connect(f2d_solver* s, int rank, int nranks, const unsigned char* up_handle64, const uint64_t* up_info4,
+                            const unsigned char* down_handle64, const uint64_t* down_info4, int cfl_cells);
 
 /* ---- headless renderers (next-row f3; read the device-resident fields, no window system) -------
  * f2d_render_density_rgba : grid_to_image_kernel (src/density_grid_renderer.cu:10-29): rows*cols RGBA8

@@ -31,9 +31,11 @@ def main():
     for n, kd, kp, halo, steps, T, graph in cases:
         fields = rng_fields(n, 5000 + n, vel_cells=4.0)  # same seed on every rank
         sl = slabmod.partition(n, world, halo, rank)
-        uid = slabmod.broadcast_unique_id(dist, rank, device=torch.device("cuda", local_rank))
-        s = slabmod.make_slab_solver(sl, n, uid, cfl_cells=6, device=local_rank, diffuse_iters=kd, project_iters=kp,
-                                     temporal_block=T, divide_mode=f2d.DIV_F64, use_graph=graph)
+        transport = os.environ.get("F2D_TRANSPORT", "p2p")
+        tdev = torch.device("cuda", local_rank)
+        uid = slabmod.broadcast_unique_id(dist, rank, device=tdev) if transport == "nccl" else None
+        s = slabmod.make_slab_solver(sl, n, uid, cfl_cells=6, device=local_rank, transport=transport, dist=dist, torch_device=tdev,
+                                     diffuse_iters=kd, project_iters=kp, temporal_block=T, divide_mode=f2d.DIV_F64, use_graph=graph)
         loc = [slabmod.take(sl, a) for a in fields]
         s.upload(*loc[:3])
         s.set_sources(*loc[3:])
@@ -63,7 +65,7 @@ def main():
             eu, ev, ed = err(glob[1], ref[1]), err(glob[2], ref[2]), err(glob[0], ref[0])
             good = eu["n_diff"] == 0 and ev["n_diff"] == 0 and ed["rel_l2"] <= 2e-6 * steps and ed["max_abs"] <= 2e-5 * steps * max(1.0, float(np.abs(ref[0]).max()))
             ok &= good
-            report.append(dict(n=n, kd=kd, kp=kp, halo=halo, steps=steps, T=T, graph=graph, world=world, exchanges=xch,
+            report.append(dict(transport=transport, n=n, kd=kd, kp=kp, halo=halo, steps=steps, T=T, graph=graph, world=world, exchanges=xch,
                                u=eu, v=ev, d=ed, ok=bool(good)))
         dist.barrier()
     if rank == 0:
