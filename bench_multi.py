@@ -49,7 +49,7 @@ def run_multi_gpu(args, workload):
     halo = int(os.environ.get("F2D_HALO", "32"))
     cfl = 8
     sl = slabmod.partition(n, world, halo, rank)
-    transport = os.environ.get("F2D_TRANSPORT", "p2p")
+    transport = os.environ.get("F2D_TRANSPORT", "auto")
     tdev = torch.device("cuda", local_rank)
     uid = slabmod.broadcast_unique_id(dist, rank, device=tdev) if transport == "nccl" else None
     solver = slabmod.make_slab_solver(sl, n, uid, cfl_cells=cfl, device=local_rank, transport=transport, dist=dist,
@@ -111,8 +111,8 @@ def run_multi_gpu(args, workload):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": workload["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload["name"], "grid": [n, n], "diffuse_iters": kd, "project_iters": kp,
-                       "parallelism": "row slabs x%d, halo %d rows, %s" % (world, halo, "direct NVLink peer stores + epoch-flag handshake in the step graph" if transport == "p2p" else "NCCL send/recv in the step graph"),
-                       "transport": transport,
+                       "parallelism": "row slabs x%d, halo %d rows, %s" % (world, halo, "direct NVLink peer stores + epoch-flag handshake in the step graph" if getattr(solver, "transport", transport) == "p2p" else "NCCL send/recv in the step graph"),
+                       "transport": getattr(solver, "transport", transport),
                        "temporal_block": int(cfg.temporal_block), "temporal_block_diffuse": int(cfg.temporal_block_diffuse), "jacobi_mode": int(cfg.jacobi_mode),
                        "divide_mode": int(cfg.divide_mode), "cfl_cells": cfl,
                        "l2": "inputs larger than L2 (slab fields of %.0f MiB)" % (sl.rows * n * 4 / 2**20)},

@@ -76,7 +76,9 @@ def gather_p2p_handles(dist, solver, world, device=None):
 
     h = (C.c_ubyte * 64)()
     info = (C.c_uint64 * 4)()
-    capi.check(capi.load().f2d_p2p_export(solver._h, h, info))
+    rc = capi.load().f2d_p2p_export(solver._h, h, info)  # a failing rank still takes part in the all-gather
+    if rc != 0:
+        info = (C.c_uint64 * 4)(0, 0, 0, 0)
     rec = torch.frombuffer(bytearray(bytes(h) + bytes(info)), dtype=torch.uint8).clone()
     if device is not None:
         rec = rec.to(device)
@@ -86,34 +88,65 @@ def gather_p2p_handles(dist, solver, world, device=None):
     for t in out:
         b = t.cpu().numpy().tobytes()
         recs.append((b[:64], np.frombuffer(b[64:96], dtype=np.uint64).copy()))
+    if any(int(r[1][3]) == 0 for r in recs):  # same verdict on every rank
+        raise capi.F2DError(capi.ERR_CUDA, "a rank could not export its CUDA IPC handle")
     return recs
 
 
-def make_slab_solver(slab, cols, unique_id=None, cfl_cells=8, device=0, transport="nccl", dist=None, torch_device=None,
+def make_slab_solver(slab, cols, unique_id=None, cfl_cells=8, device=0, transport="auto", dist=None, torch_device=None,
                      **solver_kwargs):
     """FluidSolverB200 for one slab with its halo transport wired (collective over all ranks).
+    transport="p2p" : direct peer stores over NVLink (needs dist: IPC handles are all-gathered here);
     transport="nccl": NCCL send/recv pairs (needs unique_id from broadcast_unique_id);
-    transport="p2p" : direct peer stores over NVLink (needs dist: handles are all-gathered here)."""
+    transport="auto": p2p when every rank can map its neighbours, else nccl (collective decision)."""
     s = FluidSolverB200(slab.rows, cols, global_rows=slab.global_rows, row_offset=slab.row_offset,
                         halo=slab.halo, device=device, **solver_kwargs)
     if slab.world > 1:
         L = capi.load()
-        if transport == "p2p":
-            recs = gather_p2p_handles(dist, s, slab.world, device=torch_device)
+        if transport == "auto":
+            # peer-memory transport when CUDA IPC works on every rank, else NCCL; the decision is collective
+            import torch
 
-            def arg(r):
-                if r < 0 or r >= slab.world:
-                    return None, None
-                hb, info = recs[r]
-                return (C.c_ubyte * 64).from_buffer_copy(hb), (C.c_uint64 * 4)(*[int(x) for x in info])
-
-            uh, ui = arg(slab.rank - 1)
-            dh, di = arg(slab.rank + 1)
-            capi.check(L.f2d_p2p_connect(s._h, slab.rank, slab.world, uh, ui, dh, di, cfl_cells))
-            dist.barrier()  # every rank has opened its neighbours' arenas before anyone steps
-        else:
+            ok = 1
+            try:
+                _connect_p2p(L, s, slab, dist, torch_device, cfl_cells)
+            except capi.F2DError:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=torch_device if torch_device is not None else "cpu")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 1:
+                dist.barrier()
+                s.transport = "p2p"
+                return s
+            s.close()  # some rank could not map its neighbours: everybody rebuilds with NCCL
+            s = FluidSolverB200(slab.rows, cols, global_rows=slab.global_rows, row_offset=slab.row_offset,
+                                halo=slab.halo, device=device, **solver_kwargs)
+            unique_id = broadcast_unique_id(dist, slab.rank, device=torch_device)
             capi.check(L.f2d_comm_init(s._h, unique_id, slab.rank, slab.world, cfl_cells))
+            s.transport = "nccl"
+            return s
+        if transport == "p2p":
+            _connect_p2p(L, s, slab, dist, torch_device, cfl_cells)
+            dist.barrier()  # every rank has opened its neighbours' arenas before anyone steps
+            s.transport = "p2p"
+            return s
+        capi.check(L.f2d_comm_init(s._h, unique_id, slab.rank, slab.world, cfl_cells))
+        s.transport = "nccl"
     return s
+
+
+def _connect_p2p(L, s, slab, dist, torch_device, cfl_cells):
+    recs = gather_p2p_handles(dist, s, slab.world, device=torch_device)
+
+    def arg(r):
+        if r < 0 or r >= slab.world:
+            return None, None
+        hb, info = recs[r]
+        return (C.c_ubyte * 64).from_buffer_copy(hb), (C.c_uint64 * 4)(*[int(x) for x in info])
+
+    uh, ui = arg(slab.rank - 1)
+    dh, di = arg(slab.rank + 1)
+    capi.check(L.f2d_p2p_connect(s._h, slab.rank, slab.world, uh, ui, dh, di, cfl_cells))
 
 
 def comm_exchanges(solver):

@@ -31,7 +31,7 @@ def main():
     for n, kd, kp, halo, steps, T, graph in cases:
         fields = rng_fields(n, 5000 + n, vel_cells=4.0)  # same seed on every rank
         sl = slabmod.partition(n, world, halo, rank)
-        transport = os.environ.get("F2D_TRANSPORT", "p2p")
+        transport = os.environ.get("F2D_TRANSPORT", "auto")
         tdev = torch.device("cuda", local_rank)
         uid = slabmod.broadcast_unique_id(dist, rank, device=tdev) if transport == "nccl" else None
         s = slabmod.make_slab_solver(sl, n, uid, cfl_cells=6, device=local_rank, transport=transport, dist=dist, torch_device=tdev,
