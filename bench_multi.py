@@ -80,6 +80,21 @@ def run_multi_gpu(args, workload):
     ms_max = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
 
+    fast = os.environ.get("F2D_BENCH_FAST", "0") == "1"  # weak-scaling sweeps: skip the e2e and CPU legs
+    if fast:
+        solver.close()
+        if rank == 0:
+            cells = float(n) * n
+            value = cells * args.steps / (ms_max * 1e-3)
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                              "scaling": "weak", "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": workload["name"], "grid": [n, n], "diffuse_iters": kd, "project_iters": kp,
+                                         "transport": getattr(solver, "transport", transport), "halo": halo},
+                              "gpu_launches": int(launches), "exchanges_per_step": xch / max(1, args.steps), "clocks": clocks}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     # end to end: every rank uploads its slab from pinned host memory, steps once, downloads it
     pins = [torch.from_numpy(a).pin_memory() for a in (d, u, v, sd, su, sv)]
     hd, hu, hv, hsd, hsu, hsv = [p.numpy() for p in pins]
