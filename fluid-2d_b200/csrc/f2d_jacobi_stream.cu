@@ -21,7 +21,8 @@
 //   * Input rows are staged through a per-warp shared-memory ring with 16-byte asynchronous
 //     copies (cp.async.cg -> LDGSTS, L1-bypassing), PFD rows ahead, so HBM latency is hidden
 //     without spending registers; each lane only ever reads back the bytes it copied itself,
-//     so cp.async.wait_group is the only synchronisation needed.
+//     so cp.async.wait_group is the only synchronisation needed.  Ring slots are addressed on
+//     32-bit shared addresses as ((row << 9) & mask) | aligned_base (two integer instructions).
 //   * The boundary pass (set_boundary_*, gpu.cu:11-54) is fused: domain edge columns are fixed
 //     inside the lane that holds them (columns 0/1 and N-2/N-1 share a float4 because cols%4==0),
 //     edge rows are produced by the edge rule when the adjacent interior row of the same level
@@ -30,8 +31,14 @@
 //   * Arithmetic is spelled with intrinsics (f2d_common.cuh) so every level is bit-identical to
 //     one sweep of the naive kernel: T fused sweeps == T single sweeps, bitwise.
 //   * The row loop is unrolled by RS (a multiple of 3) so that all window/ring register indices
-//     are compile-time constants; blocks of RS rows in which every level is strictly inside the
-//     chunk take a FAST path without any range or edge-row checks.
+//     are compile-time constants; a row step is one basic block; blocks of RS rows in which no
+//     level meets a GLOBAL edge row take a FAST path without range or edge-row checks.
+//   * Two fused first passes (template parameter PIN_ZERO): == 2, the first pressure pass computes
+//     the divergence from u and v on the fly (p0 == 0) and writes it out for the later passes;
+//     == 3, the first diffuse pass forms x0 = FMA(dt, source, field) (add_sources), relaxes from it
+//     and writes it out as the right-hand side of the later passes.
+//   * A host planner (launch_one) sizes the chunks from a cost model so that one launch is exactly
+//     one wave of resident warps that finish together.
 #include <algorithm>
 
 #include "f2d_kernels.cuh"
@@ -471,7 +478,11 @@ void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, in
     wpc = std::min(wpc, 4);  // __launch_bounds__(128, ...)
     const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS) + (PIN_ZERO >= 2 ? kRingP : 0)) * kLanes * sizeof(float4) +
                         (size_t)ring_r_of(T, RHS_REGS) * kLanes * sizeof(float4);  // alignment slack
-    static int occ_cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    // per device (function attributes live in the device's context) and per CTA size
+    static int occ_cache_dev[16][9] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int* occ_cache = occ_cache_dev[dev & 15];
     if (occ_cache[wpc] == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int occ = 0;

@@ -112,14 +112,6 @@ struct f2d_solver {
         for (size_t i = 0; i < temps.size(); ++i)
             if (temps[i] == p) temp_busy[i] = 0;
     }
-    void release_all() {
-        for (size_t i = 0; i < temps.size(); ++i) temp_busy[i] = 0;
-    }
-    bool is_temp(const float* p) const {
-        for (size_t i = 0; i < temps.size(); ++i)
-            if (temps[i] == p) return true;
-        return false;
-    }
 
     // ---- scalars of the reference (computed on the host exactly as it does) --------------
     size_t global_cells() const { return (size_t)g.grows * (size_t)g.cols; }
@@ -230,7 +222,7 @@ struct f2d_solver {
         }
         for (int i = 0; i < n; ++i) {
             ping[i] = acquire();
-            pong[i] = (K > 1 || true) ? acquire() : nullptr;
+            pong[i] = acquire();
             if (!ping[i] || !pong[i]) return fail(F2D_ERR_STATE, "scratch pool exhausted");
         }
         const bool stream_mode = (cfg.jacobi_mode == F2D_JACOBI_STREAM);
