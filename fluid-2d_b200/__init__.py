@@ -28,6 +28,8 @@ from .capi import (  # noqa: F401
     FIELD_V_SOURCE,
     JACOBI_NAIVE,
     JACOBI_STREAM,
+    SEM_CPU,
+    SEM_GPU,
     F2DError,
     SolverConfig,
     abi_symbols,

@@ -17,6 +17,7 @@ FIELD_PRESSURE, FIELD_DIVERGENCE = 6, 7
 BND_CONTINUOUS, BND_OPPOSITE_HORIZONTAL, BND_OPPOSITE_VERTICAL = 0, 1, 2
 JACOBI_NAIVE, JACOBI_STREAM = 0, 1
 DIV_F64, DIV_F32_CORR = 0, 1
+SEM_GPU, SEM_CPU = 0, 1
 
 
 class F2DError(RuntimeError):
@@ -44,6 +45,7 @@ class SolverConfig(C.Structure):
         ("row_offset", C.c_uint32),
         ("halo", C.c_uint32),
         ("temporal_block_diffuse", C.c_uint32),
+        ("semantics", C.c_uint32),
         ("stream", C.c_void_p),
     ]
 

@@ -1,0 +1,263 @@
+// f2d_gs.cu -- the fluid_solver_cpu-compatible stages (F2D_SEM_CPU) for sm_100a.
+//
+// fluid_solver_cpu (src/fluid_solver_cpu.cpp) differs from fluid_solver_gpu in arithmetic, not in physics:
+// in-place Gauss-Seidel relaxations (:104-113, :196-204), no FMA contraction (g++ -O2, generic x86-64), float
+// divides, corners averaged by set_boundary (:44-47), a density scatter that accumulates in lexicographic
+// source order (:127-152) and no smooth.  This file reproduces those bits on the GPU:
+//   k_gs_relax        all sweeps of a relaxation as ONE wavefront of 32x32 tiles over the in-place array
+//                     (dependencies, tile core and edge ownership: f2d_gs_tile.h), one warp per (sweep, row band),
+//                     bands chained through progress counters in global memory;
+//   k_scatter_ordered the density scatter as a gather: every target cell scans the sources that can reach it in
+//                     lexicographic order, so the float additions happen in the CPU's order (no atomics);
+//   k_max_disp        the reach of that scan (largest displacement, in cells);
+//   k_add_sources_nofma, k_advect_velocity_nofma, k_corners_avg.
+// Divergence and gradient subtract have the same operations in both reference solvers
+// (cpp:190-193, :207-211 vs gpu.cu:173-174, :202-203) and reuse the kernels of f2d_kernels_simple.cu.
+#include "f2d_gs_tile.h"
+#include "f2d_kernels.cuh"
+
+namespace f2d {
+
+namespace {
+constexpr int kGsWarps = 4;
+constexpr unsigned kSpinLimit = 1u << 24;  // polls before a wait gives up and raises the error flag (seconds)
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// lane 0: block until *flag >= need.  Bounded: a wait that never ends (a scheduling assumption broken) raises
+// *err and returns, and every other wait then returns at once, so the launch always terminates.
+__device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned need, int* err) {
+    unsigned v = ld_acquire(flag);
+    unsigned spins = 0, ns = 32;
+    while (v < need) {
+        __nanosleep(ns);
+        if (ns < 256) ns *= 2;
+        v = ld_acquire(flag);
+        if ((++spins & 255u) == 0u) {
+            if (*reinterpret_cast<volatile int*>(err)) break;
+            if (spins >= kSpinLimit) {
+                atomicExch(err, 1);
+                break;
+            }
+        }
+    }
+    return v;
+}
+}  // namespace
+
+// One warp = one (problem, sweep, row band); it marches over the column tiles of its band.  Warps take their
+// work from a ticket counter in the order (sweep, band, problem), so every dependency of a warp points to a
+// LOWER ticket, i.e. to a warp that is already running or finished: the wavefront cannot deadlock however many
+// warps the grid has and however few are resident.
+template <bool DIFFUSE>
+__global__ void __launch_bounds__(kGsWarps * 32) k_gs_relax(GsBatch b) {
+    __shared__ float smem[kGsWarps][gs::kTileFloats + gs::kRhsFloats];
+    const int lane = threadIdx.x & 31;
+    float* tile = smem[threadIdx.x >> 5];
+    float* rt = tile + gs::kTileFloats;
+
+    unsigned ticket = 0;
+    if (lane == 0) ticket = atomicAdd(b.ticket, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    const gs::Shape s = gs::make_shape(b.rows, b.cols, b.pitch);
+    if (ticket >= (unsigned)b.n * (unsigned)b.sweeps * (unsigned)s.nb) return;
+    const int f = (int)(ticket % (unsigned)b.n);
+    const unsigned rest = ticket / (unsigned)b.n;
+    const int w = (int)(rest % (unsigned)s.nb), k = (int)(rest / (unsigned)s.nb);
+
+    float* x = b.p[f].x;
+    const float* rhs = b.p[f].rhs;
+    const float a = b.p[f].a, cdiv = b.p[f].c;
+    const int kind = b.p[f].kind;
+    unsigned* done = b.flags + (size_t)f * b.sweeps * s.nb;
+    unsigned seen[3] = {0u, 0u, 0u};  // last value read from each dependency's counter (they only grow)
+
+    for (int c = 0; c < s.nt; ++c) {
+        if (lane == 0) {
+            const gs::Deps d = gs::tile_deps(s, k, w, c);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+                if (i < d.n && seen[i] < d.need[i]) seen[i] = wait_at_least(done + d.idx[i], d.need[i], b.err);
+        }
+        __syncwarp();
+        const gs::Tile t = gs::make_tile(s, w, c);
+        gs::tile_load(s, t, x, rhs, tile, rt, lane);
+        __syncwarp();
+        float west = 0.f;
+        const int nsteps = t.nr + t.nc - 1;
+        for (int step = 0; step < nsteps; ++step) {
+            gs::tile_step<DIFFUSE>(t, tile, rt, lane, step, a, cdiv, west);
+            __syncwarp();
+        }
+        gs::tile_store(s, t, kind, x, tile, lane);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release(done + (size_t)k * s.nb + w, (unsigned)(c + 1));
+    }
+}
+
+size_t gs_flag_words(int rows, int nproblems, int sweeps) {
+    const int nb = (rows - 2 + gs::kBand - 1) / gs::kBand;
+    return (size_t)nproblems * (size_t)sweeps * (size_t)nb + 1;  // + the ticket counter
+}
+
+void launch_gs_relax(const GsBatch& b, bool diffuse, cudaStream_t st) {
+    const gs::Shape s = gs::make_shape(b.rows, b.cols, b.pitch);
+    const size_t warps = (size_t)b.n * b.sweeps * s.nb;
+    const unsigned ctas = (unsigned)((warps + kGsWarps - 1) / kGsWarps);
+    if (diffuse)
+        k_gs_relax<true><<<ctas, kGsWarps * 32, 0, st>>>(b);
+    else
+        k_gs_relax<false><<<ctas, kGsWarps * 32, 0, st>>>(b);
+}
+
+// ------------------------------------------------------------------------------------ corners
+// The tail of fluid_solver_cpu::set_boundary_* (cpp:44-47, :61-64, :79-82): each corner is the mean of its two
+// edge neighbours.  Runs after a kernel that produced the edges.
+__global__ void k_corners_avg(CornerBatch b, int rows, int cols, int pitch) {
+    const int t = threadIdx.x;
+    if (t >= 4 * b.n) return;
+    float* f = b.f[t >> 2];
+    const int ci = (t & 2) ? rows - 1 : 0, cj = (t & 1) ? cols - 1 : 0;
+    const int ni = (t & 2) ? rows - 2 : 1, nj = (t & 1) ? cols - 2 : 1;
+    // 0.5f * (f(ci, nj) + f(ni, cj)): the row neighbour first, as the reference writes it
+    f[(size_t)ci * pitch + cj] = __fmul_rn(0.5f, __fadd_rn(f[(size_t)ci * pitch + nj], f[(size_t)ni * pitch + cj]));
+}
+
+void launch_corners_avg(const Geom& g, const CornerBatch& b, cudaStream_t st) {
+    k_corners_avg<<<1, 32, 0, st>>>(b, g.rows, g.cols, g.pitch);
+}
+
+// -------------------------------------------------------------------------------- add_sources
+// cpp:85-93: f += dt * s with the product rounded first (no FMA); interior only, other cells pass through.
+__global__ void __launch_bounds__(256) k_add_sources_nofma(Geom g, AddSourceBatch b, float dt) {
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (i >= g.rows || j >= g.cols) return;
+    const size_t o = (size_t)i * g.pitch + j;
+    const float* f = b.f[blockIdx.z];
+    float* out = b.o[blockIdx.z];
+    const bool interior = i >= 1 && i <= g.rows - 2 && j >= 1 && j <= g.cols - 2;
+    if (interior)
+        out[o] = __fadd_rn(f[o], __fmul_rn(dt, __ldg(b.s[blockIdx.z] + o)));
+    else if (out != f)
+        out[o] = f[o];
+}
+
+void launch_add_sources_nofma(const Geom& g, const AddSourceBatch& b, float dt, cudaStream_t st) {
+    k_add_sources_nofma<<<dim3((g.cols + 31) / 32, (g.rows + 7) / 8, b.n), dim3(32, 8), 0, st>>>(g, b, dt);
+}
+
+// ------------------------------------------------------------------------------ advect (gather)
+// cpp:153-174 for u and v in one pass (both are advected by the same copies, cpp:26-29): separate multiply and
+// subtract for the back-trace, and the bilinear form s3*(s1*a00 + s0*a01) + s2*(s1*a10 + s0*a11) without FMA.
+// Edges are produced by evaluating the inward neighbour (cpp:176), corners keep the input until k_corners_avg.
+__device__ __forceinline__ float bilinear_nofma(const Bilinear& b, float a00, float a01, float a10, float a11) {
+    const float top = __fadd_rn(__fmul_rn(b.s1, a00), __fmul_rn(b.s0, a01));
+    const float bot = __fadd_rn(__fmul_rn(b.s1, a10), __fmul_rn(b.s0, a11));
+    return __fadd_rn(__fmul_rn(b.s3, top), __fmul_rn(b.s2, bot));
+}
+
+__global__ void __launch_bounds__(256) k_advect_velocity_nofma(Geom g, const float* __restrict__ u0,
+                                                              const float* __restrict__ v0, float* __restrict__ u_out,
+                                                              float* __restrict__ v_out, float dt0) {
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    if (i >= g.rows || j >= g.cols) return;
+    const CellSrc cu = classify_cell(g, i, j, F2D_BND_OPPOSITE_HORIZONTAL);
+    const CellSrc cv = classify_cell(g, i, j, F2D_BND_OPPOSITE_VERTICAL);
+    const size_t o = (size_t)i * g.pitch + j;
+    if (cu.cls == CELL_KEEP) {
+        u_out[o] = u0[o];
+        v_out[o] = v0[o];
+        return;
+    }
+    const size_t so = (size_t)cu.si * g.pitch + cu.sj;
+    float x = __fsub_rn((float)cu.sj, __fmul_rn(dt0, __ldg(u0 + so)));
+    float y = __fsub_rn((float)cu.si, __fmul_rn(dt0, __ldg(v0 + so)));
+    x = fmaxf(1.5f, fminf((float)g.cols - 1.5f, x));
+    y = fmaxf(1.5f, fminf((float)g.rows - 1.5f, y));
+    const Bilinear b = bilinear_setup(x, y);
+    const size_t a = (size_t)b.i0 * g.pitch + b.j0;
+    const float un = bilinear_nofma(b, __ldg(u0 + a), __ldg(u0 + a + 1), __ldg(u0 + a + g.pitch), __ldg(u0 + a + g.pitch + 1));
+    const float vn = bilinear_nofma(b, __ldg(v0 + a), __ldg(v0 + a + 1), __ldg(v0 + a + g.pitch), __ldg(v0 + a + g.pitch + 1));
+    u_out[o] = apply_sign(un, cu.negate);
+    v_out[o] = apply_sign(vn, cv.negate);
+}
+
+void launch_advect_velocity_nofma(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out, float dt0,
+                                  cudaStream_t st) {
+    k_advect_velocity_nofma<<<dim3((g.cols + 31) / 32, (g.rows + 7) / 8), dim3(32, 8), 0, st>>>(g, u0, v0, u_out, v_out, dt0);
+}
+
+// ----------------------------------------------------------------------- advect (ordered scatter)
+// Largest forward displacement max(|dt0*u|, |dt0*v|) over the interior, as the bit pattern of a non-negative
+// float (integer max == float max there; a NaN compares above everything and widens the scan to the grid).
+__global__ void __launch_bounds__(256) k_max_disp(Geom g, const float* __restrict__ u, const float* __restrict__ v, float dt0,
+                                                 unsigned* bits) {
+    unsigned m = 0u;
+    for (int i = 1 + blockIdx.y * 8 + threadIdx.y; i <= g.rows - 2; i += gridDim.y * 8)
+        for (int j = 1 + blockIdx.x * 32 + threadIdx.x; j <= g.cols - 2; j += gridDim.x * 32) {
+            const size_t o = (size_t)i * g.pitch + j;
+            m = max(m, __float_as_uint(fabsf(__fmul_rn(dt0, __ldg(u + o)))));
+            m = max(m, __float_as_uint(fabsf(__fmul_rn(dt0, __ldg(v + o)))));
+        }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (threadIdx.x == 0 && m) atomicMax(bits, m);
+}
+
+// cpp:127-152 turned inside out.  The reference zeroes the field, then walks the sources (i,j) in lexicographic
+// order and adds four weighted copies of each into the cells around its forward-traced position.  A target cell
+// therefore receives its contributions in lexicographic SOURCE order, and float addition makes that order part of
+// the result.  Here one thread owns one interior target cell and visits, in the same order, every source whose
+// displacement can reach it (|di|, |dj| <= R = ceil(max displacement) + 1), recomputing the source's landing
+// point exactly as the reference does (product rounded, then added) and adding its share if it lands here.
+// Edge cells and corners are overwritten by the boundary pass that follows (cpp:176), so only the interior is
+// produced.
+__global__ void __launch_bounds__(256) k_scatter_ordered(Geom g, const float* __restrict__ src, const float* __restrict__ u,
+                                                        const float* __restrict__ v, float* __restrict__ out, float dt0,
+                                                        const unsigned* __restrict__ disp_bits) {
+    const int tj = 1 + blockIdx.x * 32 + threadIdx.x, ti = 1 + blockIdx.y * 8 + threadIdx.y;
+    if (ti > g.rows - 2 || tj > g.cols - 2) return;
+    const float md = __uint_as_float(*disp_bits);
+    const int far = max(g.rows, g.cols);
+    const int R = (md < (float)far) ? (int)ceilf(md) + 1 : far;  // also catches NaN / inf
+    const int ilo = max(1, ti - R), ihi = min(g.rows - 2, ti + R);
+    const int jlo = max(1, tj - R), jhi = min(g.cols - 2, tj + R);
+    const float xmax = (float)g.cols - 1.5f, ymax = (float)g.rows - 1.5f;
+    float acc = 0.f;
+    for (int i = ilo; i <= ihi; ++i) {
+        const size_t row = (size_t)i * g.pitch;
+        for (int j = jlo; j <= jhi; ++j) {
+            const float y = __fadd_rn((float)i, __fmul_rn(dt0, __ldg(v + row + j)));
+            if (y < 0.5f || y > ymax) continue;
+            const int di = ti - (int)y;
+            if ((unsigned)di > 1u) continue;
+            const float x = __fadd_rn((float)j, __fmul_rn(dt0, __ldg(u + row + j)));
+            if (x < 0.5f || x > xmax) continue;
+            const int dj = tj - (int)x;
+            if ((unsigned)dj > 1u) continue;
+            const Bilinear b = bilinear_setup(x, y);
+            const float wx = dj ? b.s0 : b.s1, wy = di ? b.s2 : b.s3;
+            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wx, wy), __ldg(src + row + j)));
+        }
+    }
+    out[(size_t)ti * g.pitch + tj] = acc;
+}
+
+void launch_scatter_ordered(const Geom& g, const float* src, const float* u, const float* v, float* out, float dt0,
+                            unsigned* disp_bits, cudaStream_t st) {
+    cudaMemsetAsync(disp_bits, 0, sizeof(unsigned), st);
+    const dim3 bl(32, 8);
+    const dim3 gr_red(min((g.cols + 31) / 32, 64), min((g.rows + 7) / 8, 256));
+    k_max_disp<<<gr_red, bl, 0, st>>>(g, u, v, dt0, disp_bits);
+    k_scatter_ordered<<<dim3((g.cols - 2 + 31) / 32, (g.rows - 2 + 7) / 8), bl, 0, st>>>(g, src, u, v, out, dt0, disp_bits);
+}
+
+}  // namespace f2d

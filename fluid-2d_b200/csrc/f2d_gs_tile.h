@@ -1,0 +1,185 @@
+// f2d_gs_tile.h -- tile core of the Gauss-Seidel wavefront (the fluid_solver_cpu-compatible relaxation).
+//
+// fluid_solver_cpu relaxes IN PLACE in lexicographic order (src/fluid_solver_cpu.cpp:104-113 diffuse,
+// :196-204 pressure): cell (i,j) of sweep k reads the sweep-k values of (i-1,j), (i,j-1) and the
+// sweep-(k-1) values of (i+1,j), (i,j+1), then set_boundary runs (cpp:112, :203).  Any execution order that
+// respects those four dependencies produces the same bits, so the grid is cut into tiles of kBand rows x
+// kTileCols columns and tile T(k, w, c) (sweep k, row band w, column tile c) may run as soon as
+//     T(k, w-1, c)   wrote the row above it        (new north values),
+//     T(k, w, c-1)   wrote the column left of it    (new west values; the same warp's previous tile),
+//     T(k-1, w+1, c) wrote the row below it         (old south values),
+//     T(k-1, w, c+1) wrote the column right of it   (old east values; implies T(k-1, w, c)),
+// i.e. the tiles of ALL sweeps form one wavefront  tau = w + c + 2k  and run concurrently on one in-place
+// array.  The same four conditions also cover the write-after-read hazards (a tile overwrites sweep-(k-1)
+// values only after every reader of them has finished).  Inside a tile the 32 lanes of a warp own one row
+// each and march along the columns skewed by one step per row (lane l handles column t - l at step t).
+//
+// Edge cells belong to the tile whose interior cells they mirror: a tile that touches row 1 / row R-2 /
+// column 1 / column C-2 also writes row 0 / R-1 / column 0 / C-1 with the sign of the boundary kind
+// (cpp:33-83 without the corners), so the next sweep reads them like any other neighbour.  The four corners
+// are never read by a 5-point stencil; they are averaged once after the last sweep (k_corners_avg).
+//
+// This header is plain C++ on purpose: the CUDA kernel (f2d_gs.cu) calls the functions below with
+// lane = threadIdx.x % 32 and __syncwarp() between steps, and tests/gs_emul.cpp compiles the SAME functions
+// with g++ and runs the tiles in random dependency-respecting orders against the sequential sweep (no GPU needed).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define F2D_HD __host__ __device__ __forceinline__
+#else
+#define F2D_HD inline
+#endif
+
+namespace f2d {
+namespace gs {
+
+constexpr int kBand = 32;                          // rows per band == lanes of a warp
+constexpr int kTileCols = 32;                      // interior columns per tile
+constexpr int kTP = kTileCols + 2;                 // pitch of the value tile; kTP - 1 is odd: skewed accesses hit 32 banks
+constexpr int kTileFloats = (kBand + 2) * kTP;     // value tile with a one-cell frame
+constexpr int kRhsFloats = kBand * kTileCols;      // right-hand side tile (pitch kTileCols: 31 * l + t, conflict-free)
+
+// boundary kinds as in include/f2d.h
+constexpr int kBndContinuous = 0, kBndOppositeHorizontal = 1, kBndOppositeVertical = 2;
+
+struct Shape {
+    int rows, cols, pitch;  // field extent and row pitch in floats
+    int nb, nt;             // row bands, column tiles
+};
+
+F2D_HD Shape make_shape(int rows, int cols, int pitch) {
+    Shape s;
+    s.rows = rows;
+    s.cols = cols;
+    s.pitch = pitch;
+    s.nb = (rows - 2 + kBand - 1) / kBand;
+    s.nt = (cols - 2 + kTileCols - 1) / kTileCols;
+    return s;
+}
+
+struct Tile {
+    int i0, nr;  // first interior row of the band, rows in it (1..kBand)
+    int j0, nc;  // first interior column of the tile, columns in it (1..kTileCols)
+};
+
+F2D_HD Tile make_tile(const Shape& s, int w, int c) {
+    Tile t;
+    t.i0 = 1 + kBand * w;
+    t.nr = s.rows - 1 - t.i0;
+    if (t.nr > kBand) t.nr = kBand;
+    t.j0 = 1 + kTileCols * c;
+    t.nc = s.cols - 1 - t.j0;
+    if (t.nc > kTileCols) t.nc = kTileCols;
+    return t;
+}
+
+// ---- progress flags ---------------------------------------------------------------------------------
+// done[(k * nb + w)] = number of column tiles band w has finished in sweep k (one block of K * nb words per
+// problem).  Before tile c the warp of (k, w) waits for up to three counters:
+struct Deps {
+    int n;
+    int idx[3];        // index into the problem's flag block
+    unsigned need[3];  // minimal value
+};
+
+F2D_HD Deps tile_deps(const Shape& s, int k, int w, int c) {
+    Deps d;
+    d.n = 0;
+    if (w > 0) {  // north row: T(k, w-1, c)
+        d.idx[d.n] = k * s.nb + (w - 1);
+        d.need[d.n++] = (unsigned)(c + 1);
+    }
+    if (k > 0) {
+        if (w + 1 < s.nb) {  // south row: T(k-1, w+1, c)
+            d.idx[d.n] = (k - 1) * s.nb + (w + 1);
+            d.need[d.n++] = (unsigned)(c + 1);
+        }
+        // east column: T(k-1, w, c+1); the last tile only needs its own previous sweep
+        d.idx[d.n] = (k - 1) * s.nb + w;
+        d.need[d.n++] = (unsigned)((c + 2 < s.nt) ? c + 2 : s.nt);
+    }
+    return d;
+}
+
+// ---- arithmetic (g++: -ffp-contract=off; nvcc: intrinsics, the library is built with -fmad=false anyway) ----
+#if defined(__CUDA_ARCH__)
+F2D_HD float fadd(float a, float b) { return __fadd_rn(a, b); }
+F2D_HD float fmul(float a, float b) { return __fmul_rn(a, b); }
+F2D_HD float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+F2D_HD float ld_iter(const float* p) { return __ldcg(p); }  // iterate: written by other SMs, read at L2
+F2D_HD float ld_rhs(const float* p) { return __ldg(p); }    // right-hand side: read-only for the whole launch
+#else
+F2D_HD float fadd(float a, float b) { return a + b; }
+F2D_HD float fmul(float a, float b) { return a * b; }
+F2D_HD float fdiv(float a, float b) { return a / b; }
+F2D_HD float ld_iter(const float* p) { return *p; }
+F2D_HD float ld_rhs(const float* p) { return *p; }
+#endif
+
+// diffuse (cpp:107-108): (x0 + a * (((N + S) + W) + E)) / (1.f + 4.f * a), product and sum rounded separately
+F2D_HD float diffuse_cell(float n, float s, float w, float e, float x0, float a, float c) {
+    float sum = fadd(fadd(fadd(n, s), w), e);
+    return fdiv(fadd(x0, fmul(a, sum)), c);
+}
+// pressure (cpp:199-200): ((((div + E) + W) + S) + N) / 4.0f
+F2D_HD float pressure_cell(float n, float s, float w, float e, float dv) {
+    return fdiv(fadd(fadd(fadd(fadd(dv, e), w), s), n), 4.0f);
+}
+
+// ---- the three phases of one tile, per lane ------------------------------------------------------------
+// Phase 1: bring the (nr + 2) x (nc + 2) frame of the iterate and the nr x nc right-hand side on chip.
+F2D_HD void tile_load(const Shape& s, const Tile& t, const float* x, const float* rhs, float* tile, float* rt, int lane) {
+    const float* xr = x + (size_t)(t.i0 - 1) * s.pitch + (t.j0 - 1);
+    for (int r = 0; r < t.nr + 2; ++r) {
+        for (int q = lane; q < t.nc + 2; q += 32) tile[r * kTP + q] = ld_iter(xr + q);
+        xr += s.pitch;
+    }
+    const float* br = rhs + (size_t)t.i0 * s.pitch + t.j0;
+    for (int r = 0; r < t.nr; ++r) {
+        if (lane < t.nc) rt[r * kTileCols + lane] = ld_rhs(br + lane);
+        br += s.pitch;
+    }
+}
+
+// Phase 2, step t = 0 .. nr + nc - 2: lane l updates cell (row l, column t - l) of the tile.  `west` carries the
+// lane's previous result (the new west neighbour).  A step only reads cells that were written in EARLIER steps
+// (north: lane l-1 at step t-1) or that are still old (south, east), so lanes never conflict within a step.
+template <bool DIFFUSE>
+F2D_HD void tile_step(const Tile& t, float* tile, const float* rt, int lane, int step, float a, float c, float& west) {
+    const int q = step - lane;
+    if (lane >= t.nr || q < 0 || q >= t.nc) return;
+    float* cell = tile + (lane + 1) * kTP + (q + 1);
+    const float n = cell[-kTP], s = cell[kTP], e = cell[1];
+    const float w = (q == 0) ? cell[-1] : west;
+    const float r = rt[lane * kTileCols + q];
+    const float v = DIFFUSE ? diffuse_cell(n, s, w, e, r, a, c) : pressure_cell(n, s, w, e, r);
+    *cell = v;
+    west = v;
+}
+
+F2D_HD float signed_copy(float v, bool negate) { return negate ? -v : v; }
+
+// Phase 3: write the nr x nc results back, plus the edge cells this tile owns.
+F2D_HD void tile_store(const Shape& s, const Tile& t, int kind, float* x, const float* tile, int lane) {
+    const bool neg_rows = (kind == kBndOppositeVertical);    // top / bottom rows negate (v)
+    const bool neg_cols = (kind == kBndOppositeHorizontal);  // left / right columns negate (u)
+    float* xr = x + (size_t)t.i0 * s.pitch + t.j0;
+    for (int r = 0; r < t.nr; ++r) {
+        if (lane < t.nc) xr[lane] = tile[(r + 1) * kTP + lane + 1];
+        xr += s.pitch;
+    }
+    if (lane < t.nc) {
+        if (t.i0 == 1) x[t.j0 + lane] = signed_copy(tile[1 * kTP + lane + 1], neg_rows);
+        if (t.i0 + t.nr == s.rows - 1)
+            x[(size_t)(s.rows - 1) * s.pitch + t.j0 + lane] = signed_copy(tile[t.nr * kTP + lane + 1], neg_rows);
+    }
+    if (lane < t.nr) {
+        float* row = x + (size_t)(t.i0 + lane) * s.pitch;
+        if (t.j0 == 1) row[0] = signed_copy(tile[(lane + 1) * kTP + 1], neg_cols);
+        if (t.j0 + t.nc == s.cols - 1) row[s.cols - 1] = signed_copy(tile[(lane + 1) * kTP + t.nc], neg_cols);
+    }
+}
+
+}  // namespace gs
+}  // namespace f2d

@@ -48,6 +48,36 @@ void launch_smooth_bnd(const Geom& g, const float* in, float* out, bool do_smoot
 void launch_smooth_plain(const Geom& g, const float* in, float* out, cudaStream_t st);
 void launch_set_bnd_inplace(const Geom& g, float* f, int kind, cudaStream_t st);
 
+// ---- fluid_solver_cpu-compatible stages (F2D_SEM_CPU; f2d_gs.cu) -------------------------------
+// One in-place Gauss-Seidel problem: x = relax(x, rhs), `sweeps` lexicographic sweeps with the edge rule of `kind`.
+struct GsProblem {
+    float* x;          // iterate, updated in place (edges included, corners not)
+    const float* rhs;  // x0 (diffuse) or the divergence (pressure); must not alias x
+    float a, c;        // diffuse: x = (rhs + a*sum4) / c with c = 1.f + 4.f*a in fp32 (cpp:108); unused for pressure
+    int kind;          // F2D_BND_*
+};
+struct GsBatch {
+    GsProblem p[kMaxBatch];
+    int n, sweeps;
+    int rows, cols, pitch;
+    unsigned* flags;   // n * sweeps * bands progress counters, zeroed before the launch ...
+    unsigned* ticket;  // ... and the work counter right behind them (gs_flag_words() words in total)
+    int* err;          // raised if a wait timed out (reported by f2d_sync)
+};
+struct CornerBatch {
+    float* f[2 * kMaxBatch];
+    int n;
+};
+size_t gs_flag_words(int rows, int nproblems, int sweeps);
+void launch_gs_relax(const GsBatch& b, bool diffuse, cudaStream_t st);
+void launch_corners_avg(const Geom& g, const CornerBatch& b, cudaStream_t st);
+void launch_add_sources_nofma(const Geom& g, const AddSourceBatch& b, float dt, cudaStream_t st);
+void launch_advect_velocity_nofma(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out, float dt0,
+                                  cudaStream_t st);
+// density scatter in the CPU solver's summation order; writes the interior of `out` only.  disp_bits: one device word.
+void launch_scatter_ordered(const Geom& g, const float* src, const float* u, const float* v, float* out, float dt0,
+                            unsigned* disp_bits, cudaStream_t st);
+
 // ---- peer-to-peer halo exchange (f2d_p2p.cu)
 struct XchgSeg {
     const float4* src;  // my rows

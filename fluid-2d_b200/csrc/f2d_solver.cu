@@ -98,6 +98,11 @@ struct f2d_solver {
     bool fuse_sources = true;     // F2D_FUSE_SOURCES=0: separate add_sources kernel (A/B, cross-check)
     bool fuse_divergence = true;  // F2D_FUSE_DIVERGENCE=0: separate divergence kernel (A/B, cross-check)
     std::vector<void*> registered;  // host ranges this solver page-locked (cudaHostRegister)
+    // F2D_SEM_CPU (fluid_solver_cpu-compatible arithmetic, f2d_gs.cu)
+    unsigned* gs_flags = nullptr;  // progress counters + ticket of the Gauss-Seidel wavefront
+    size_t gs_flag_cap = 0;        // words allocated
+    unsigned* gs_aux = nullptr;    // [0] wavefront error flag, [1] scatter reach (float bits)
+    bool cpu_sem() const { return cfg.semantics == F2D_SEM_CPU; }
 
     // ---- scratch pool -------------------------------------------------------------------
     float* acquire() {
@@ -454,6 +459,168 @@ struct f2d_solver {
         return F2D_OK;
     }
 
+    // ================================================================ F2D_SEM_CPU: fluid_solver_cpu, bit for bit
+    float dt0_cpu(float dt) const { return sqrtf((float)global_cells()) * dt; }  // cpp:126 (float sqrt, float product)
+
+    int ensure_gs_flags(size_t words) {
+        if (words <= gs_flag_cap) return F2D_OK;
+        if (capturing) return fail(F2D_ERR_STATE, "Gauss-Seidel flag block too small inside a graph capture");
+        F2D_CUDA(cudaStreamSynchronize(stream));
+        if (gs_flags) cudaFree(gs_flags);
+        gs_flags = nullptr;
+        gs_flag_cap = 0;
+        F2D_CUDA(cudaMalloc(&gs_flags, words * sizeof(unsigned)));
+        gs_flag_cap = words;
+        return F2D_OK;
+    }
+
+    int corners(std::initializer_list<float*> fields) {
+        CornerBatch cb;
+        cb.n = 0;
+        for (float* f : fields) cb.f[cb.n++] = f;
+        launch_corners_avg(g, cb, stream);
+        count();
+        F2D_CUDA(cudaGetLastError());
+        return F2D_OK;
+    }
+
+    // K in-place lexicographic Gauss-Seidel sweeps of n fields (one wavefront launch), each followed by the
+    // boundary pass of its kind (cpp:104-113 / :196-204); the corners are averaged once at the end, which is
+    // what K boundary passes leave behind (no stencil reads a corner in between).
+    int relax_gs(int n, float* const* x, const float* const* rhs, const int* kinds, const float* a, bool diffuse, uint32_t K) {
+        if (K == 0) return F2D_OK;
+        const size_t words = gs_flag_words(g.rows, n, (int)K);
+        F2D_TRY(ensure_gs_flags(words));
+        F2D_CUDA(cudaMemsetAsync(gs_flags, 0, words * sizeof(unsigned), stream));
+        GsBatch b;
+        b.n = n;
+        b.sweeps = (int)K;
+        b.rows = g.rows;
+        b.cols = g.cols;
+        b.pitch = g.pitch;
+        b.flags = gs_flags;
+        b.ticket = gs_flags + (words - 1);
+        b.err = reinterpret_cast<int*>(gs_aux);
+        CornerBatch cb;
+        cb.n = n;
+        for (int i = 0; i < n; ++i) {
+            b.p[i].x = x[i];
+            b.p[i].rhs = rhs[i];
+            b.p[i].a = a ? a[i] : 0.f;
+            b.p[i].c = a ? 1.f + 4.f * a[i] : 1.f;  // cpp:108, fp32
+            b.p[i].kind = kinds[i];
+            cb.f[i] = x[i];
+        }
+        launch_gs_relax(b, diffuse, stream);
+        count();
+        launch_corners_avg(g, cb, stream);
+        count();
+        F2D_CUDA(cudaGetLastError());
+        return F2D_OK;
+    }
+
+    // diffuse (cpp:95-114) of n fields in place: x0 <- field, K sweeps
+    int diffuse_cpu(int n, float* const* x, const int* kinds, const float* rates, float dt, uint32_t K) {
+        if (K == 0) return F2D_OK;
+        float* x0[kMaxBatch] = {nullptr, nullptr, nullptr};
+        const float* rhs[kMaxBatch];
+        float a[kMaxBatch];
+        for (int i = 0; i < n; ++i) {
+            x0[i] = acquire();
+            if (!x0[i]) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+            F2D_CUDA(cudaMemcpyAsync(x0[i], x[i], field_bytes, cudaMemcpyDeviceToDevice, stream));  // cpp:102
+            rhs[i] = x0[i];
+            a[i] = diffuse_coef(rates[i], dt).a;  // cpp:100, the same fp32 expression as gpu.cu:79
+        }
+        int rc = relax_gs(n, x, rhs, kinds, a, true, K);
+        for (int i = 0; i < n; ++i) release(x0[i]);
+        return rc;
+    }
+
+    // project (cpp:179-215): (u_in, v_in) -> (u_out, v_out), all distinct buffers
+    int project_cpu(const float* u_in, const float* v_in, float* u_out, float* v_out, uint32_t K) {
+        if (last_div) release(last_div);
+        if (last_p) release(last_p);
+        last_div = last_p = nullptr;
+        float *dv = acquire(), *p = acquire();
+        if (!dv || !p) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        launch_divergence(g, u_in, v_in, dv, h(), stream);  // cpp:190-193 + edges of :195
+        count();
+        F2D_TRY(corners({dv}));
+        F2D_CUDA(cudaMemsetAsync(p, 0, field_bytes, stream));  // cpp:186
+        float* px[1] = {p};
+        const float* prhs[1] = {dv};
+        const int kind[1] = {F2D_BND_CONTINUOUS};
+        F2D_TRY(relax_gs(1, px, prhs, kind, nullptr, false, K));
+        launch_gradient(g, p, u_in, v_in, u_out, v_out, h(), stream);  // cpp:207-211 + edges of :213-214
+        count();
+        F2D_TRY(corners({u_out, v_out}));
+        last_div = dv;
+        last_p = p;
+        return F2D_OK;
+    }
+
+    // density advect (cpp:127-152 + :176): f <- scatter of f by (u, v) with the boundary pass.  `do_smooth` adds
+    // fluid_solver_gpu's density smooth (gpu.cu:314-323); fluid_solver_cpu has none.
+    int advect_density_cpu(float* f, const float* u, const float* v, float dt, bool do_smooth) {
+        float* sc = acquire();
+        if (!sc) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        launch_scatter_ordered(g, f, u, v, sc, dt0_cpu(dt), gs_aux + 1, stream);  // interior of sc
+        count(2);
+        launch_smooth_bnd(g, sc, f, do_smooth, stream);  // edges from the scattered interior, out of place
+        count();
+        release(sc);
+        return corners({f});
+    }
+
+    // One full fluid_solver_cpu::solve step (cpp:15-30) on the device-resident state.
+    int enqueue_step_cpu(float diffusion_rate, float viscosity, float dt) {
+        float *d = state[F2D_FIELD_DENSITY], *u = state[F2D_FIELD_U], *v = state[F2D_FIELD_V];
+        float *us = acquire(), *vs = acquire();
+        if (!us || !vs) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        // add_sources (cpp:16, :21-22).  u and v go out of place: the density advect below needs the pre-step u, v
+        AddSourceBatch ab;
+        ab.n = 3;
+        ab.f[0] = d;
+        ab.o[0] = d;
+        ab.s[0] = state[F2D_FIELD_DENSITY_SOURCE];
+        ab.f[1] = u;
+        ab.o[1] = us;
+        ab.s[1] = state[F2D_FIELD_U_SOURCE];
+        ab.f[2] = v;
+        ab.o[2] = vs;
+        ab.s[2] = state[F2D_FIELD_V_SOURCE];
+        launch_add_sources_nofma(g, ab, dt, stream);
+        count();
+        // the three diffuses (cpp:17, :23-24) share one wavefront launch
+        {
+            float* x[3] = {d, us, vs};
+            const int kind[3] = {F2D_BND_CONTINUOUS, F2D_BND_OPPOSITE_HORIZONTAL, F2D_BND_OPPOSITE_VERTICAL};
+            const float rates[3] = {diffusion_rate, viscosity, viscosity};
+            F2D_TRY(diffuse_cpu(3, x, kind, rates, dt, cfg.diffuse_iters));
+        }
+        // density advect by the pre-step velocity (cpp:18)
+        F2D_TRY(advect_density_cpu(d, u, v, dt, cfg.smooth != 0));
+        if (capturing)
+            F2D_CUDA(cudaEventRecordWithFlags(ev_density, stream, cudaEventRecordExternal));
+        else
+            F2D_CUDA(cudaEventRecord(ev_density, stream));
+        // velocity: project, self-advect, project (cpp:25-30)
+        float *u2 = acquire(), *v2 = acquire();
+        if (!u2 || !v2) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        F2D_TRY(project_cpu(us, vs, u2, v2, cfg.project_iters));
+        launch_advect_velocity_nofma(g, u2, v2, us, vs, dt0_cpu(dt), stream);  // cpp:26-29
+        count();
+        F2D_TRY(corners({us, vs}));
+        release(u2);
+        release(v2);
+        F2D_TRY(project_cpu(us, vs, u, v, cfg.project_iters));
+        release(us);
+        release(vs);
+        F2D_CUDA(cudaGetLastError());
+        return F2D_OK;
+    }
+
     // rows of the local slab whose cells this solver owns (halo rows excluded)
     int own_begin() const { return (g.grow0 == 0) ? 0 : (int)cfg.halo; }
     int own_end() const { return (g.grow0 + g.rows == g.grows) ? g.rows : g.rows - (int)cfg.halo; }
@@ -475,7 +642,7 @@ struct f2d_solver {
         // relaxed mode: NCCL (multi-GPU) may issue its own runtime calls while we capture
         F2D_CUDA(cudaStreamBeginCapture(stream, multi() ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
         capturing = true;
-        int rc = enqueue_step(diffusion_rate, viscosity, dt);
+        int rc = cpu_sem() ? enqueue_step_cpu(diffusion_rate, viscosity, dt) : enqueue_step(diffusion_rate, viscosity, dt);
         capturing = false;
         cudaError_t ce = cudaStreamEndCapture(stream, &graph);
         if (rc != F2D_OK) {
@@ -503,7 +670,8 @@ struct f2d_solver {
                 exchanges += exchanges_in_graph;
             }
         } else {
-            for (uint32_t s = 0; s < nsteps; ++s) F2D_TRY(enqueue_step(diffusion_rate, viscosity, dt));
+            for (uint32_t s = 0; s < nsteps; ++s)
+                F2D_TRY(cpu_sem() ? enqueue_step_cpu(diffusion_rate, viscosity, dt) : enqueue_step(diffusion_rate, viscosity, dt));
         }
         return F2D_OK;
     }
@@ -746,6 +914,7 @@ F2D_API int f2d_p2p_connect(f2d_solver* s, int rank, int nranks, const unsigned 
                             const unsigned char* down_handle64, const uint64_t* down_info4, int cfl_cells) {
     if (!s) return fail(F2D_ERR_INVALID, "NULL argument");
     if (nranks < 2 || rank < 0 || rank >= nranks) return fail(F2D_ERR_INVALID, "bad rank/nranks");
+    if (s->cpu_sem()) return fail(F2D_ERR_INVALID, "F2D_SEM_CPU runs on one GPU only");
     if (s->cfg.halo == 0) return fail(F2D_ERR_INVALID, "a slab solver needs halo > 0");
     if (s->multi()) return fail(F2D_ERR_STATE, "communicator already initialised");
     if ((s->g.grow0 > 0) != (rank > 0) || (s->g.grow0 + s->g.rows < s->g.grows) != (rank < nranks - 1))
@@ -795,6 +964,7 @@ F2D_API int f2d_comm_unique_id(char* id128) {
 F2D_API int f2d_comm_init(f2d_solver* s, const char* id128, int rank, int nranks, int cfl_cells) {
     if (!s || !id128) return fail(F2D_ERR_INVALID, "NULL argument");
     if (nranks < 2 || rank < 0 || rank >= nranks) return fail(F2D_ERR_INVALID, "bad rank/nranks");
+    if (s->cpu_sem()) return fail(F2D_ERR_INVALID, "F2D_SEM_CPU runs on one GPU only");
     if (s->cfg.halo == 0) return fail(F2D_ERR_INVALID, "a slab solver needs halo > 0");
     if (s->comm) return fail(F2D_ERR_STATE, "communicator already initialised");
     if ((s->g.grow0 > 0) != (rank > 0) || (s->g.grow0 + s->g.rows < s->g.grows) != (rank < nranks - 1))
@@ -885,6 +1055,9 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
         return fail(F2D_ERR_INVALID, "unknown jacobi_mode");
     if (cfg->divide_mode != F2D_DIV_F64 && cfg->divide_mode != F2D_DIV_F32_CORR)
         return fail(F2D_ERR_INVALID, "unknown divide_mode");
+    if (cfg->semantics != F2D_SEM_GPU && cfg->semantics != F2D_SEM_CPU) return fail(F2D_ERR_INVALID, "unknown semantics");
+    if (cfg->semantics == F2D_SEM_CPU && (cfg->halo != 0 || cfg->row_offset != 0 || grows != cfg->rows))
+        return fail(F2D_ERR_INVALID, "F2D_SEM_CPU runs on one GPU only (the Gauss-Seidel wavefront is not split into slabs)");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -920,7 +1093,10 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
         s->cfg.temporal_block_diffuse =
             s->cfg.temporal_block ? s->cfg.temporal_block : (uint32_t)env_int("F2D_TEMPORAL_BLOCK_DIFFUSE", env_int("F2D_TEMPORAL_BLOCK", auto_T));
     if (s->cfg.temporal_block == 0) s->cfg.temporal_block = (uint32_t)env_int("F2D_TEMPORAL_BLOCK", auto_T);
-    if (s->cfg.jacobi_mode == F2D_JACOBI_STREAM) {
+    if (s->cfg.semantics == F2D_SEM_CPU) {
+        s->cfg.jacobi_mode = F2D_JACOBI_NAIVE;  // unused: the relaxations are Gauss-Seidel wavefronts
+        s->cfg.temporal_block = s->cfg.temporal_block_diffuse = 1;
+    } else if (s->cfg.jacobi_mode == F2D_JACOBI_STREAM) {
         if (!stream_supported(s->g, (int)s->cfg.temporal_block) || !stream_supported(s->g, (int)s->cfg.temporal_block_diffuse)) {
             delete s;
             return fail(F2D_ERR_INVALID,
@@ -970,6 +1146,14 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
         return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
     cudaMemsetAsync(s->oob_flag, 0, sizeof(int), s->stream);
     s->host_register = env_int("F2D_HOST_REGISTER", 1) != 0;
+    if (s->cpu_sem()) {
+        const uint32_t k = std::max(3u * s->cfg.diffuse_iters, s->cfg.project_iters);
+        s->gs_flag_cap = gs_flag_words(s->g.rows, 1, (int)std::max(k, 1u));
+        if (cudaMalloc(&s->gs_flags, s->gs_flag_cap * sizeof(unsigned)) != cudaSuccess ||
+            cudaMalloc(&s->gs_aux, 4 * sizeof(unsigned)) != cudaSuccess)
+            return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
+        cudaMemsetAsync(s->gs_aux, 0, 4 * sizeof(unsigned), s->stream);
+    }
     if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_density, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming) != cudaSuccess)
@@ -992,6 +1176,8 @@ F2D_API void f2d_destroy(f2d_solver* s) {
     if (s->arena) cudaFree(s->arena);
     if (s->oob_flag) cudaFree(s->oob_flag);
     if (s->render_buf) cudaFree(s->render_buf);
+    if (s->gs_flags) cudaFree(s->gs_flags);
+    if (s->gs_aux) cudaFree(s->gs_aux);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     if (s->peer_up.arena) cudaIpcCloseMemHandle(s->peer_up.arena);
     if (s->peer_down.arena) cudaIpcCloseMemHandle(s->peer_down.arena);
@@ -1094,6 +1280,14 @@ F2D_API int f2d_sync(f2d_solver* s) {
         F2D_CUDA(cudaMemcpy(&err, s->flags + 2, sizeof(unsigned), cudaMemcpyDeviceToHost));
         if (err) return fail(F2D_ERR_STATE, "halo exchange timed out waiting for a neighbour GPU");
     }
+    if (s->gs_aux) {
+        unsigned err = 0;
+        F2D_CUDA(cudaMemcpy(&err, s->gs_aux, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if (err) {
+            cudaMemset(s->gs_aux, 0, sizeof(unsigned));
+            return fail(F2D_ERR_STATE, "Gauss-Seidel wavefront: a tile waited for its neighbours for too long (results invalid)");
+        }
+    }
     if (oob) {
         cudaMemset(s->oob_flag, 0, sizeof(int));
         return fail(F2D_ERR_STATE, "density scatter left the slab: displacement exceeded the halo (CFL bound violated)");
@@ -1141,6 +1335,7 @@ F2D_API int f2d_stage_set_bnd(f2d_solver* s, int field, int kind) {
     launch_set_bnd_inplace(s->g, s->state[field], kind, s->stream);
     s->count();
     F2D_CUDA(cudaGetLastError());
+    if (s->cpu_sem()) return s->corners({s->state[field]});  // cpp:44-47
     return F2D_OK;
 }
 
@@ -1152,7 +1347,10 @@ F2D_API int f2d_stage_add_sources(f2d_solver* s, int field, float dt) {
     ab.f[0] = s->state[field];
     ab.o[0] = s->state[field];
     ab.s[0] = s->state[field + 3];
-    launch_add_sources(s->g, ab, dt, s->stream);
+    if (s->cpu_sem())
+        launch_add_sources_nofma(s->g, ab, dt, s->stream);  // cpp:85-93
+    else
+        launch_add_sources(s->g, ab, dt, s->stream);
     s->count();
     F2D_CUDA(cudaGetLastError());
     return F2D_OK;
@@ -1161,6 +1359,12 @@ F2D_API int f2d_stage_add_sources(f2d_solver* s, int field, float dt) {
 F2D_API int f2d_stage_diffuse(f2d_solver* s, int field, int kind, float rate, float dt, uint32_t iters) {
     F2D_NEED(s);
     if (field < 0 || field > F2D_FIELD_V) return fail(F2D_ERR_INVALID, "bad field");
+    if (s->cpu_sem()) {  // cpp:95-114
+        float* x[1] = {s->state[field]};
+        const int kinds[1] = {kind};
+        const float rates[1] = {rate};
+        return s->diffuse_cpu(1, x, kinds, rates, dt, iters);
+    }
     const float* in[1] = {s->state[field]};
     const float* rhs[1] = {s->state[field]};
     const int kinds[1] = {kind};
@@ -1191,6 +1395,7 @@ F2D_API int f2d_stage_smooth(f2d_solver* s) {
 F2D_API int f2d_stage_advect_density(f2d_solver* s, float dt) {
     F2D_NEED(s);
     float* d = s->state[F2D_FIELD_DENSITY];
+    if (s->cpu_sem()) return s->advect_density_cpu(d, s->state[F2D_FIELD_U], s->state[F2D_FIELD_V], dt, false);  // cpp:116-177
     float* sc = s->acquire();
     if (!sc) return fail(F2D_ERR_STATE, "scratch pool exhausted");
     F2D_CUDA(cudaMemsetAsync(sc, 0, s->field_bytes, s->stream));
@@ -1211,11 +1416,15 @@ F2D_API int f2d_stage_advect_velocity(f2d_solver* s, float dt) {
     if (!u0 || !v0) return fail(F2D_ERR_STATE, "scratch pool exhausted");
     F2D_TRY(copy_back(s, u0, u));  // gpu.cu:248-249
     F2D_TRY(copy_back(s, v0, v));
-    launch_advect_velocity(s->g, u0, v0, u, v, s->dt0(dt), s->own_begin(), s->own_end(), s->oob_flag, s->stream);
+    if (s->cpu_sem())
+        launch_advect_velocity_nofma(s->g, u0, v0, u, v, s->dt0_cpu(dt), s->stream);  // cpp:26-29
+    else
+        launch_advect_velocity(s->g, u0, v0, u, v, s->dt0(dt), s->own_begin(), s->own_end(), s->oob_flag, s->stream);
     s->count();
     s->release(u0);
     s->release(v0);
     F2D_CUDA(cudaGetLastError());
+    if (s->cpu_sem()) return s->corners({u, v});
     return F2D_OK;
 }
 
@@ -1226,7 +1435,7 @@ F2D_API int f2d_stage_project(f2d_solver* s, uint32_t iters) {
     if (!u0 || !v0) return fail(F2D_ERR_STATE, "scratch pool exhausted");
     F2D_TRY(copy_back(s, u0, u));
     F2D_TRY(copy_back(s, v0, v));
-    int rc = s->project(u0, v0, u, v, iters);
+    int rc = s->cpu_sem() ? s->project_cpu(u0, v0, u, v, iters) : s->project(u0, v0, u, v, iters);
     s->release(u0);
     s->release(v0);
     return rc;
@@ -1235,6 +1444,30 @@ F2D_API int f2d_stage_project(f2d_solver* s, uint32_t iters) {
 F2D_API int f2d_bench_jacobi(f2d_solver* s, int diffuse_like, uint32_t iters, uint32_t reps, float* elapsed_ms) {
     F2D_NEED(s);
     if (!elapsed_ms || reps == 0) return fail(F2D_ERR_INVALID, "bad arguments");
+    if (s->cpu_sem()) {
+        // the Gauss-Seidel wavefront on a scratch copy: x = copy of u (diffuse) or zero (pressure), rhs = density
+        float* x = s->acquire();
+        if (!x) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        if (diffuse_like)
+            F2D_CUDA(cudaMemcpyAsync(x, s->state[F2D_FIELD_U], s->field_bytes, cudaMemcpyDeviceToDevice, s->stream));
+        else
+            F2D_CUDA(cudaMemsetAsync(x, 0, s->field_bytes, s->stream));
+        float* xs[1] = {x};
+        const float* rhs1[1] = {s->state[F2D_FIELD_DENSITY]};
+        const int kinds1[1] = {F2D_BND_CONTINUOUS};
+        const float a1[1] = {s->diffuse_coef(1e-6f, 0.02f).a};
+        int rc = s->relax_gs(1, xs, rhs1, kinds1, diffuse_like ? a1 : nullptr, diffuse_like != 0, iters);  // warm-up
+        if (rc == F2D_OK && cudaStreamSynchronize(s->stream) == cudaSuccess) {
+            cudaEventRecord(s->ev0, s->stream);
+            for (uint32_t r = 0; r < reps && rc == F2D_OK; ++r)
+                rc = s->relax_gs(1, xs, rhs1, kinds1, diffuse_like ? a1 : nullptr, diffuse_like != 0, iters);
+            cudaEventRecord(s->ev1, s->stream);
+            if (rc == F2D_OK && (cudaEventSynchronize(s->ev1) != cudaSuccess || cudaEventElapsedTime(elapsed_ms, s->ev0, s->ev1) != cudaSuccess))
+                rc = fail(F2D_ERR_CUDA, "timing the Gauss-Seidel wavefront failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        s->release(x);
+        return rc;
+    }
     // scratch problem: rhs = density state, start = u state (diffuse) or zero (pressure)
     const float* in[1] = {diffuse_like ? s->state[F2D_FIELD_U] : nullptr};
     const float* rhs[1] = {s->state[F2D_FIELD_DENSITY]};

@@ -24,11 +24,20 @@ def _host(a, writable=False):
 
 
 class FluidSolverB200:
-    """Drop-in for fluid_solver_gpu on one B200 (or one row slab of a multi-GPU run)."""
+    """Drop-in for fluid_solver_gpu on one B200 (or one row slab of a multi-GPU run).
+
+    `semantics=capi.SEM_CPU` switches the arithmetic to fluid_solver_cpu's (in-place Gauss-Seidel, no FMA,
+    averaged corners, ordered scatter; src/fluid_solver_cpu.cpp): with diffuse_iters=project_iters=20 and
+    smooth=False the results are bit-identical to fluid_solver_cpu::solve.  See `cpu_compatible`."""
+
+    @classmethod
+    def cpu_compatible(cls, rows, cols, iters=20, **kw):
+        """The solver configured as fluid_solver_cpu::solve (src/fluid_solver_cpu.cpp:15-30)."""
+        return cls(rows, cols, diffuse_iters=iters, project_iters=iters, smooth=False, semantics=capi.SEM_CPU, **kw)
 
     def __init__(self, rows, cols, diffuse_iters=15, project_iters=20, smooth=True, jacobi_mode=None,
                  temporal_block=0, temporal_block_diffuse=0, divide_mode=capi.DIV_F32_CORR, use_graph=True, device=-1,
-                 global_rows=None, row_offset=0, halo=0, stream=None):
+                 global_rows=None, row_offset=0, halo=0, stream=None, semantics=capi.SEM_GPU):
         self._h = C.c_void_p()
         L = capi.load()
         cfg = capi.SolverConfig()
@@ -47,6 +56,7 @@ class FluidSolverB200:
         cfg.row_offset = row_offset
         cfg.halo = halo
         cfg.stream = stream
+        cfg.semantics = semantics
         capi.check(L.f2d_create(C.byref(cfg), C.byref(self._h)))
         self._L = L
         self.rows, self.cols = rows, cols

@@ -10,9 +10,10 @@
  * a time (the reference solver is not re-entrant either: member temp buffers,
  * src/fluid_solver_gpu.cuh:62-68).
  *
- * Arithmetic contract: the results follow fluid_solver_gpu (true Jacobi, edges
- * without corners, density `smooth`); iteration counts
+ * Arithmetic contract: by default the results follow fluid_solver_gpu (true Jacobi,
+ * edges without corners, density `smooth`); iteration counts
  * are parameters instead of the literals 15/20 (src/fluid_solver_gpu.cu:238-252).
+ * With f2d_config.semantics = F2D_SEM_CPU they follow fluid_solver_cpu bit for bit.
  *
  * The C++ adapter `fluid_solver_b200` (include/fluid_solver_b200.hpp) and the
  * Python host mirror (fluid-2d_b200/solver.py) are thin layers over these calls.
@@ -27,7 +28,7 @@
 extern "C" {
 #endif
 
-#define F2D_ABI_VERSION 1
+#define F2D_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define F2D_API __attribute__((visibility("default")))
@@ -67,6 +68,15 @@ extern "C" {
 #define F2D_DIV_F64 0      /* (float)((double)num / (1.0 + 4.0*a)): the reference's own arithmetic */
 #define F2D_DIV_F32_CORR 1 /* fp32 reciprocal + two-term FMA residual correction (default)          */
 
+/* which of the reference's two solvers the arithmetic follows (they are NOT numerically equivalent,
+ * SURVEY.md Appendix B) */
+#define F2D_SEM_GPU 0 /* fluid_solver_gpu (src/fluid_solver_gpu.cu): Jacobi, FMA where nvcc contracts, corners untouched,
+                         density smooth, atomics in the scatter (default)                                            */
+#define F2D_SEM_CPU 1 /* fluid_solver_cpu (src/fluid_solver_cpu.cpp): in-place lexicographic Gauss-Seidel, no FMA, float
+                         divides, averaged corners, scatter summed in source order.  Bit-identical to that solver,
+                         density included.  Single GPU; set diffuse_iters = project_iters = 20 and smooth = 0 to get
+                         exactly fluid_solver_cpu::solve (cpp:15-30)                                                  */
+
 typedef struct f2d_solver f2d_solver; /* opaque: owns device fields, stream, graphs */
 
 typedef struct f2d_config {
@@ -87,6 +97,7 @@ typedef struct f2d_config {
     uint32_t row_offset;
     uint32_t halo;
     uint32_t temporal_block_diffuse; /* same for the diffuse solve; 0 = auto (temporal_block if set, else as above) */
+    uint32_t semantics;      /* F2D_SEM_*; jacobi_mode, temporal_block* and divide_mode only apply to F2D_SEM_GPU */
     void* stream; /* cudaStream_t to run on; NULL = the solver creates its own                  */
 } f2d_config;
 

@@ -27,7 +27,17 @@ public:
         unsigned project_iterations = 20;  // src/fluid_solver_gpu.cu:247,252
         bool smooth = true;                // src/fluid_solver_gpu.cu:240
         bool exact_divide = false;         // true: the reference's fp64 divide in diffuse (bit-exact u, v)
+        bool cpu_semantics = false;        // true: fluid_solver_cpu's arithmetic (F2D_SEM_CPU), bit-identical to it
         int device = -1;
+
+        // the configuration that reproduces fluid_solver_cpu::solve bit for bit (src/fluid_solver_cpu.cpp:15-30)
+        static options cpu_compatible() {
+            options o;
+            o.diffuse_iterations = o.project_iterations = 20;
+            o.smooth = false;
+            o.cpu_semantics = true;
+            return o;
+        }
     };
 
     fluid_solver_b200(size_t const rows, size_t const cols) : fluid_solver_b200(rows, cols, options{}) {}
@@ -39,6 +49,7 @@ public:
         cfg.project_iters = opt.project_iterations;
         cfg.smooth = opt.smooth ? 1u : 0u;
         cfg.divide_mode = opt.exact_divide ? F2D_DIV_F64 : F2D_DIV_F32_CORR;
+        cfg.semantics = opt.cpu_semantics ? F2D_SEM_CPU : F2D_SEM_GPU;
         cfg.device = opt.device;
         check(f2d_create(&cfg, &handle_));
     }

@@ -27,13 +27,14 @@ def test_library_contains_sm100a_code(f2d):
 
 def test_abi_version_and_default_config(f2d):
     L = f2d.load()
-    assert L.f2d_abi_version() == 1
+    assert L.f2d_abi_version() == 2
     cfg = f2d.SolverConfig()
     assert L.f2d_config_default(C.byref(cfg), 256, 256) == 0
     assert cfg.struct_size == C.sizeof(f2d.SolverConfig)
     # defaults == fluid_solver_gpu::solve literals (src/fluid_solver_gpu.cu:238-252)
     assert (cfg.diffuse_iters, cfg.project_iters, cfg.smooth) == (15, 20, 1)
     assert cfg.jacobi_mode == f2d.JACOBI_STREAM and cfg.global_rows == 256
+    assert cfg.semantics == f2d.SEM_GPU  # fluid_solver_gpu arithmetic unless asked otherwise
 
 
 def test_create_without_gpu_raises_no_fallback(f2d):
