@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(kGsWarps * 32) k_gs_relax(GsBatch b) {
     unsigned* done = b.flags + (size_t)f * b.sweeps * s.nb;
     unsigned seen[3] = {0u, 0u, 0u};  // last value read from each dependency's counter (they only grow)
 
+    float pf[gs::kPf];  // the next tile's interior + right-hand side, in flight while the current tile computes
     for (int c = 0; c < s.nt; ++c) {
         if (lane == 0) {
             const gs::Deps d = gs::tile_deps(s, k, w, c);
@@ -88,8 +89,13 @@ __global__ void __launch_bounds__(kGsWarps * 32) k_gs_relax(GsBatch b) {
         }
         __syncwarp();
         const gs::Tile t = gs::make_tile(s, w, c);
-        gs::tile_load(s, t, x, rhs, tile, rt, lane);
+        if (c == 0) gs::tile_prefetch(s, t, x, rhs, pf, lane);  // nothing was prefetched for the band's first tile
+        const gs::Frame fr = gs::tile_frame_load(s, t, x, tile, lane, c == 0);
+        __syncwarp();  // every lane has read the previous tile's last column
+        gs::tile_commit(t, pf, tile, rt, lane);
+        gs::tile_frame_store(t, fr, tile, lane);
         __syncwarp();
+        if (c + 1 < s.nt) gs::tile_prefetch(s, gs::make_tile(s, w, c + 1), x, rhs, pf, lane);
         float west = 0.f;
         const int nsteps = t.nr + t.nc - 1;
         for (int step = 0; step < nsteps; ++step) {

@@ -122,23 +122,83 @@ F2D_HD float diffuse_cell(float n, float s, float w, float e, float x0, float a,
     float sum = fadd(fadd(fadd(n, s), w), e);
     return fdiv(fadd(x0, fmul(a, sum)), c);
 }
-// pressure (cpp:199-200): ((((div + E) + W) + S) + N) / 4.0f
+// pressure (cpp:199-200): ((((div + E) + W) + S) + N) / 4.0f.  Dividing by 4 and multiplying by 0.25 round the same
+// real number, so the product is bit-identical (subnormal results included) and skips the divide sequence.
 F2D_HD float pressure_cell(float n, float s, float w, float e, float dv) {
-    return fdiv(fadd(fadd(fadd(fadd(dv, e), w), s), n), 4.0f);
+    return fmul(fadd(fadd(fadd(fadd(dv, e), w), s), n), 0.25f);
 }
 
-// ---- the three phases of one tile, per lane ------------------------------------------------------------
-// Phase 1: bring the (nr + 2) x (nc + 2) frame of the iterate and the nr x nc right-hand side on chip.
-F2D_HD void tile_load(const Shape& s, const Tile& t, const float* x, const float* rhs, float* tile, float* rt, int lane) {
-    const float* xr = x + (size_t)(t.i0 - 1) * s.pitch + (t.j0 - 1);
-    for (int r = 0; r < t.nr + 2; ++r) {
-        for (int q = lane; q < t.nc + 2; q += 32) tile[r * kTP + q] = ld_iter(xr + q);
-        xr += s.pitch;
+// ---- the phases of one tile, per lane -------------------------------------------------------------------
+// Phase 1 brings the (nr + 2) x (nc + 2) frame of the iterate and the nr x nc right-hand side on chip.  It is
+// split so that the bulk never sits on the critical path:
+//   tile_prefetch   the tile's INTERIOR old values and right-hand side -> registers (lane = column, one register
+//                   per row).  They are final as soon as T(k-1, w, c) is done, which the wait of tile c-1
+//                   already established (its east condition), so the loads are issued before tile c-1 computes
+//                   and land while it does;
+//   tile_frame_*    after the tile's own wait: the row above, the row below and the column right of the tile
+//                   (one batch of loads); the column left of it is the previous tile's last column, still in
+//                   shared memory (from global for the first tile);
+//   tile_commit     registers -> shared memory.
+constexpr int kPf = 2 * kBand;  // prefetch registers per lane
+
+F2D_HD void tile_prefetch(const Shape& s, const Tile& t, const float* x, const float* rhs, float* pf, int lane) {
+    const size_t o = (size_t)t.i0 * s.pitch + t.j0 + lane;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < kBand; ++r) {
+        const bool ok = (r < t.nr) && (lane < t.nc);
+        pf[r] = ok ? ld_iter(x + o + (size_t)r * s.pitch) : 0.f;
+        pf[kBand + r] = ok ? ld_rhs(rhs + o + (size_t)r * s.pitch) : 0.f;
     }
-    const float* br = rhs + (size_t)t.i0 * s.pitch + t.j0;
-    for (int r = 0; r < t.nr; ++r) {
-        if (lane < t.nc) rt[r * kTileCols + lane] = ld_rhs(br + lane);
-        br += s.pitch;
+}
+
+struct Frame {
+    float top0, top1, bot0, bot1, right, left;
+};
+
+// `first` : the band's first tile (left column from global); otherwise `tile` still holds the previous tile.
+F2D_HD Frame tile_frame_load(const Shape& s, const Tile& t, const float* x, const float* tile, int lane, bool first) {
+    Frame f;
+    const float* top = x + (size_t)(t.i0 - 1) * s.pitch + (t.j0 - 1);
+    const float* bot = x + (size_t)(t.i0 + t.nr) * s.pitch + (t.j0 - 1);
+    const bool hi = (kBand + lane < t.nc + 2);  // lanes 0, 1 also fetch frame columns 32, 33
+    f.top0 = (lane < t.nc + 2) ? ld_iter(top + lane) : 0.f;
+    f.top1 = hi ? ld_iter(top + kBand + lane) : 0.f;
+    f.bot0 = (lane < t.nc + 2) ? ld_iter(bot + lane) : 0.f;
+    f.bot1 = hi ? ld_iter(bot + kBand + lane) : 0.f;
+    const float* row = x + (size_t)(t.i0 + lane) * s.pitch;
+    f.right = (lane < t.nr) ? ld_iter(row + t.j0 + t.nc) : 0.f;
+    f.left = 0.f;
+    if (lane < t.nr) f.left = first ? ld_iter(row + t.j0 - 1) : tile[(lane + 1) * kTP + kTileCols];
+    return f;
+}
+
+F2D_HD void tile_commit(const Tile& t, const float* pf, float* tile, float* rt, int lane) {
+    if (lane >= t.nc) return;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int r = 0; r < kBand; ++r)
+        if (r < t.nr) {
+            tile[(r + 1) * kTP + lane + 1] = pf[r];
+            rt[r * kTileCols + lane] = pf[kBand + r];
+        }
+}
+
+F2D_HD void tile_frame_store(const Tile& t, const Frame& f, float* tile, int lane) {
+    const bool hi = (kBand + lane < t.nc + 2);
+    if (lane < t.nc + 2) {
+        tile[lane] = f.top0;
+        tile[(t.nr + 1) * kTP + lane] = f.bot0;
+    }
+    if (hi) {
+        tile[kBand + lane] = f.top1;
+        tile[(t.nr + 1) * kTP + kBand + lane] = f.bot1;
+    }
+    if (lane < t.nr) {
+        tile[(lane + 1) * kTP] = f.left;
+        tile[(lane + 1) * kTP + t.nc + 1] = f.right;
     }
 }
 

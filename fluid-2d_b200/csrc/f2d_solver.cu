@@ -98,6 +98,20 @@ struct f2d_solver {
     bool fuse_sources = true;     // F2D_FUSE_SOURCES=0: separate add_sources kernel (A/B, cross-check)
     bool fuse_divergence = true;  // F2D_FUSE_DIVERGENCE=0: separate divergence kernel (A/B, cross-check)
     std::vector<void*> registered;  // host ranges this solver page-locked (cudaHostRegister)
+    // solve() pipeline (single GPU): the step cut into four parts, each launched as soon as ITS inputs are uploaded
+    //   part 0: add_sources + diffuse u   (needs u, su)      part 2: project, advect, project   (needs parts 0, 1)
+    //   part 1: add_sources + diffuse v   (needs v, sv)      part 3: the density chain          (needs d, sd, u, v)
+    // The new velocity lands in out_u / out_v (pool buffers held for the life of the solver), so that part 3 still
+    // finds the pre-step u, v in the state buffers; it is copied into the state after part 3.
+    bool host_pipeline = true;  // F2D_HOST_PIPELINE=0: upload everything, one step graph, download (A/B)
+    cudaStream_t up_stream = nullptr;
+    cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_vel = nullptr, ev_fence = nullptr;
+    cudaGraphExec_t host_exec[4] = {nullptr, nullptr, nullptr, nullptr};
+    GraphKey host_key = {0.f, 0.f, 0.f, false};
+    uint64_t host_kernels[4] = {0, 0, 0, 0};
+    float *out_u = nullptr, *out_v = nullptr;
+    float* hp_x0[2] = {nullptr, nullptr};         // add_sources outputs of u, v (alive from part 0/1 to part 2)
+    const float* hp_res[2] = {nullptr, nullptr};  // diffused u, v
     // F2D_SEM_CPU (fluid_solver_cpu-compatible arithmetic, f2d_gs.cu)
     unsigned* gs_flags = nullptr;  // progress counters + ticket of the Gauss-Seidel wavefront
     size_t gs_flag_cap = 0;        // words allocated
@@ -621,6 +635,187 @@ struct f2d_solver {
         return F2D_OK;
     }
 
+    // ================================================================ solve() pipeline parts (single GPU, F2D_SEM_GPU)
+    int enqueue_host_part(int part, float diffusion_rate, float viscosity, float dt) {
+        float *d = state[F2D_FIELD_DENSITY], *u = state[F2D_FIELD_U], *v = state[F2D_FIELD_V];
+        const bool fuse_src = fuse_sources && cfg.jacobi_mode == F2D_JACOBI_STREAM && cfg.diffuse_iters > 0;
+        if (part == 0 || part == 1) {  // gpu.cu:243-246 for one velocity component
+            const int fld = (part == 0) ? F2D_FIELD_U : F2D_FIELD_V;
+            const int kind[1] = {part == 0 ? F2D_BND_OPPOSITE_HORIZONTAL : F2D_BND_OPPOSITE_VERTICAL};
+            const DiffuseCoef kc[1] = {diffuse_coef(viscosity, dt)};
+            float* x0 = acquire();
+            if (!x0) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+            const float* x0c[1] = {x0};
+            const float* res[1];
+            if (fuse_src) {
+                const float* in[1] = {state[fld]};
+                const float* srcs[1] = {state[fld + 3]};
+                F2D_TRY(relax(1, in, x0c, kind, kc, true, cfg.diffuse_iters, res, srcs, dt));
+            } else {
+                AddSourceBatch ab;
+                ab.n = 1;
+                ab.f[0] = state[fld];
+                ab.o[0] = x0;
+                ab.s[0] = state[fld + 3];
+                launch_add_sources(g, ab, dt, stream);
+                count();
+                F2D_TRY(relax(1, x0c, x0c, kind, kc, true, cfg.diffuse_iters, res));
+            }
+            hp_x0[part] = x0;
+            hp_res[part] = res[0];
+            return F2D_OK;
+        }
+        if (part == 2) {  // gpu.cu:247-252
+            const float *u1 = hp_res[0], *v1 = hp_res[1];
+            if (u1 != hp_x0[0]) release(hp_x0[0]);
+            if (v1 != hp_x0[1]) release(hp_x0[1]);
+            float *u2 = acquire(), *v2 = acquire();
+            if (!u2 || !v2) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+            F2D_TRY(project(u1, v1, u2, v2, cfg.project_iters));
+            float *u3 = const_cast<float*>(u1), *v3 = const_cast<float*>(v1);
+            launch_advect_velocity(g, u2, v2, u3, v3, dt0(dt), own_begin(), own_end(), oob_flag, stream);
+            count();
+            release(u2);
+            release(v2);
+            F2D_TRY(project(u3, v3, out_u, out_v, cfg.project_iters));
+            release(u3);
+            release(v3);
+            hp_x0[0] = hp_x0[1] = nullptr;
+            hp_res[0] = hp_res[1] = nullptr;
+            F2D_CUDA(cudaGetLastError());
+            return F2D_OK;
+        }
+        // part 3: add_sources + diffuse + scatter + smooth of the density (gpu.cu:237-240), by the PRE-step u, v
+        const int kind[1] = {F2D_BND_CONTINUOUS};
+        const DiffuseCoef kc[1] = {diffuse_coef(diffusion_rate, dt)};
+        float* ds = fuse_src ? acquire() : d;
+        if (!ds) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        const float* x0c[1] = {ds};
+        const float* dif[1];
+        if (fuse_src) {
+            const float* in[1] = {d};
+            const float* srcs[1] = {state[F2D_FIELD_DENSITY_SOURCE]};
+            F2D_TRY(relax(1, in, x0c, kind, kc, true, cfg.diffuse_iters, dif, srcs, dt));
+        } else {
+            AddSourceBatch ab;
+            ab.n = 1;
+            ab.f[0] = d;
+            ab.o[0] = d;
+            ab.s[0] = state[F2D_FIELD_DENSITY_SOURCE];
+            launch_add_sources(g, ab, dt, stream);
+            count();
+            F2D_TRY(relax(1, x0c, x0c, kind, kc, true, cfg.diffuse_iters, dif));
+        }
+        float* sc = acquire();
+        if (!sc) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        F2D_CUDA(cudaMemsetAsync(sc, 0, field_bytes, stream));
+        launch_scatter_density(g, dif[0], u, v, sc, dt0(dt), own_begin(), own_end(), oob_flag, stream);
+        count();
+        if (dif[0] != d) release(dif[0]);
+        if (ds != d) release(ds);
+        launch_smooth_bnd(g, sc, d, cfg.smooth != 0, stream);
+        count();
+        release(sc);
+        F2D_CUDA(cudaGetLastError());
+        return F2D_OK;
+    }
+
+    int ensure_host_graphs(float diffusion_rate, float viscosity, float dt) {
+        if (host_exec[0] && host_key.valid && host_key.diffusion_rate == diffusion_rate && host_key.viscosity == viscosity &&
+            host_key.dt == dt)
+            return F2D_OK;
+        for (auto& e : host_exec) {
+            if (e) cudaGraphExecDestroy(e);
+            e = nullptr;
+        }
+        host_key.valid = false;
+        if (last_div) release(last_div);
+        if (last_p) release(last_p);
+        last_div = last_p = nullptr;
+        for (int part = 0; part < 4; ++part) {
+            const uint64_t before = launches;
+            cudaGraph_t graph = nullptr;
+            F2D_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            capturing = true;
+            int rc = enqueue_host_part(part, diffusion_rate, viscosity, dt);
+            capturing = false;
+            cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+            host_kernels[part] = launches - before;
+            launches = before;
+            if (rc != F2D_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (ce != cudaSuccess) return fail(F2D_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+            ce = cudaGraphInstantiate(&host_exec[part], graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) return fail(F2D_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ce));
+        }
+        host_key = {diffusion_rate, viscosity, dt, true};
+        return F2D_OK;
+    }
+
+    int run_host_part(int part, float diffusion_rate, float viscosity, float dt) {
+        if (!cfg.use_graph) return enqueue_host_part(part, diffusion_rate, viscosity, dt);
+        F2D_CUDA(cudaGraphLaunch(host_exec[part], stream));
+        launches += host_kernels[part];
+        return F2D_OK;
+    }
+
+    int h2d_on(float* dst, const float* src, cudaStream_t st) {
+        return cudaMemcpy2DAsync(dst, (size_t)g.pitch * sizeof(float), src, (size_t)g.cols * sizeof(float),
+                                 (size_t)g.cols * sizeof(float), (size_t)g.rows, cudaMemcpyHostToDevice, st) == cudaSuccess
+                   ? F2D_OK
+                   : fail(F2D_ERR_CUDA, "cudaMemcpy2DAsync(H2D) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+
+    // fluid_solver::solve with the uploads, the four parts of the step and the downloads overlapped: the copy
+    // engines run in both directions while the SMs work on whatever already arrived.
+    int solve_host_pipelined(float* density, const float* density_source, float diffusion_rate, float* u, float* v,
+                             const float* u_source, const float* v_source, float viscosity, float dt) {
+        if (!out_u) {
+            out_u = acquire();
+            out_v = acquire();
+            if (!out_u || !out_v) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        }
+        if (cfg.use_graph) F2D_TRY(ensure_host_graphs(diffusion_rate, viscosity, dt));
+        // uploads, in the order the parts need them (whatever is queued on the solver stream goes first)
+        F2D_CUDA(cudaEventRecord(ev_fence, stream));
+        F2D_CUDA(cudaStreamWaitEvent(up_stream, ev_fence, 0));
+        F2D_TRY(h2d_on(state[F2D_FIELD_U], u, up_stream));
+        F2D_TRY(h2d_on(state[F2D_FIELD_U_SOURCE], u_source, up_stream));
+        F2D_CUDA(cudaEventRecord(ev_in[0], up_stream));
+        F2D_TRY(h2d_on(state[F2D_FIELD_V], v, up_stream));
+        F2D_TRY(h2d_on(state[F2D_FIELD_V_SOURCE], v_source, up_stream));
+        F2D_CUDA(cudaEventRecord(ev_in[1], up_stream));
+        F2D_TRY(h2d_on(state[F2D_FIELD_DENSITY_SOURCE], density_source, up_stream));
+        F2D_TRY(h2d_on(state[F2D_FIELD_DENSITY], density, up_stream));
+        F2D_CUDA(cudaEventRecord(ev_in[2], up_stream));
+        // compute
+        F2D_CUDA(cudaStreamWaitEvent(stream, ev_in[0], 0));
+        F2D_TRY(run_host_part(0, diffusion_rate, viscosity, dt));
+        F2D_CUDA(cudaStreamWaitEvent(stream, ev_in[1], 0));
+        F2D_TRY(run_host_part(1, diffusion_rate, viscosity, dt));
+        F2D_TRY(run_host_part(2, diffusion_rate, viscosity, dt));
+        F2D_CUDA(cudaEventRecord(ev_vel, stream));
+        F2D_CUDA(cudaStreamWaitEvent(stream, ev_in[2], 0));
+        F2D_TRY(run_host_part(3, diffusion_rate, viscosity, dt));
+        F2D_CUDA(cudaEventRecord(ev_density, stream));
+        // the device-resident state follows the host grids: u, v <- the new velocity
+        F2D_CUDA(cudaMemcpyAsync(state[F2D_FIELD_U], out_u, field_bytes, cudaMemcpyDeviceToDevice, stream));
+        F2D_CUDA(cudaMemcpyAsync(state[F2D_FIELD_V], out_v, field_bytes, cudaMemcpyDeviceToDevice, stream));
+        // downloads: velocity as soon as part 2 is done (the density chain is still running), then the density
+        F2D_CUDA(cudaStreamWaitEvent(copy_stream, ev_vel, 0));
+        F2D_TRY(d2h_on(u, out_u, copy_stream));
+        F2D_TRY(d2h_on(v, out_v, copy_stream));
+        F2D_CUDA(cudaStreamWaitEvent(copy_stream, ev_density, 0));
+        F2D_TRY(d2h_on(density, state[F2D_FIELD_DENSITY], copy_stream));
+        F2D_CUDA(cudaEventRecord(ev_copy, copy_stream));
+        F2D_CUDA(cudaStreamWaitEvent(stream, ev_copy, 0));  // nothing queued later may overtake the downloads
+        F2D_CUDA(cudaStreamSynchronize(copy_stream));
+        return F2D_OK;
+    }
+
     // rows of the local slab whose cells this solver owns (halo rows excluded)
     int own_begin() const { return (g.grow0 == 0) ? 0 : (int)cfg.halo; }
     int own_end() const { return (g.grow0 + g.rows == g.grows) ? g.rows : g.rows - (int)cfg.halo; }
@@ -1127,7 +1322,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     // One arena for everything peers may touch: 6 state fields, the scratch pool, the two landing zones of
     // the reverse (scatter) exchange and a flag block.  One allocation == one CUDA IPC handle per rank, and a
     // buffer is identified across ranks by its index (every rank runs the same schedule on the same pool).
-    const int ntemps = 11;  // deepest point: batched diffuse (3 x0 + 3x2 ping-pong + p/div views)
+    const int ntemps = 13;  // deepest point: batched diffuse (3 x0 + 3x2 ping-pong + p/div views) + out_u/out_v of the solve() pipeline
     s->field_stride = (s->field_bytes + 511) / 512 * 512;
     s->rx_bytes = ((size_t)cfg->halo * s->g.pitch * sizeof(float) + 511) / 512 * 512;
     s->arena_bytes = (size_t)(6 + ntemps) * s->field_stride + 2 * s->rx_bytes + 4096;
@@ -1158,6 +1353,14 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
         cudaEventCreateWithFlags(&s->ev_density, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming) != cudaSuccess)
         return cleanup(fail(F2D_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    if (cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_in[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_in[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_in[2], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_vel, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_fence, cudaEventDisableTiming) != cudaSuccess)
+        return cleanup(fail(F2D_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    s->host_pipeline = env_int("F2D_HOST_PIPELINE", 1) != 0;
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
         return cleanup(fail(F2D_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaStreamSynchronize(s->stream) != cudaSuccess)
@@ -1171,6 +1374,16 @@ F2D_API void f2d_destroy(f2d_solver* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    for (auto& e : s->host_exec)
+        if (e) cudaGraphExecDestroy(e);
+    if (s->up_stream) {
+        cudaStreamSynchronize(s->up_stream);
+        cudaStreamDestroy(s->up_stream);
+    }
+    for (auto& e : s->ev_in)
+        if (e) cudaEventDestroy(e);
+    if (s->ev_vel) cudaEventDestroy(s->ev_vel);
+    if (s->ev_fence) cudaEventDestroy(s->ev_fence);
     for (int i = 0; i < 6; ++i)
         s->state[i] = nullptr;
     if (s->arena) cudaFree(s->arena);
@@ -1302,6 +1515,10 @@ F2D_API int f2d_solve_host(f2d_solver* s, float* density, const float* density_s
     const size_t host_bytes = (size_t)s->g.rows * s->g.cols * sizeof(float);
     const void* hosts[6] = {density, u, v, density_source, u_source, v_source};
     for (const void* h : hosts) s->pin_host(h, host_bytes);
+    if (s->host_pipeline && !s->multi() && !s->cpu_sem()) {
+        F2D_TRY(s->solve_host_pipelined(density, density_source, diffusion_rate, u, v, u_source, v_source, viscosity, dt));
+        return f2d_sync(s);
+    }
     // upload (gpu.cu:232-234 and the source uploads of :281) -> one step -> download (:255-257)
     F2D_TRY(s->h2d(s->state[F2D_FIELD_DENSITY], density));
     F2D_TRY(s->h2d(s->state[F2D_FIELD_DENSITY_SOURCE], density_source));

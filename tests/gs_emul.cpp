@@ -22,16 +22,34 @@ uint64_t next_rand(uint64_t& s) {
     return x ^ (x >> 31);
 }
 
+// on-chip state of one warp = one (sweep, band): shared-memory tiles and the prefetch registers of its 32 lanes
+struct Band {
+    float tile[kTileFloats], rt[kRhsFloats];
+    float pf[32][kPf];
+    Band() {
+        for (int i = 0; i < kTileFloats; ++i) tile[i] = -12345.0f;  // poison: an unloaded cell must never be used
+        for (int i = 0; i < kRhsFloats; ++i) rt[i] = -54321.0f;
+    }
+};
+
 template <bool DIFFUSE>
-void run_tile(const Shape& s, int w, int c, int kind, float* x, const float* rhs, float a, float cc) {
-    float tile[kTileFloats], rt[kRhsFloats], west[32];
-    for (int i = 0; i < kTileFloats; ++i) tile[i] = -12345.0f;  // poison: an unloaded cell must never be used
+void run_tile(const Shape& s, Band& b, int w, int c, int kind, float* x, const float* rhs, float a, float cc) {
+    float west[32];
+    Frame fr[32];
     const Tile t = make_tile(s, w, c);
-    for (int lane = 0; lane < 32; ++lane) tile_load(s, t, x, rhs, tile, rt, lane);
+    if (c == 0)  // the first tile has nothing prefetched: fetch now (after the wait)
+        for (int lane = 0; lane < 32; ++lane) tile_prefetch(s, t, x, rhs, b.pf[lane], lane);
+    for (int lane = 0; lane < 32; ++lane) fr[lane] = tile_frame_load(s, t, x, b.tile, lane, c == 0);
+    for (int lane = 0; lane < 32; ++lane) tile_commit(t, b.pf[lane], b.tile, b.rt, lane);
+    for (int lane = 0; lane < 32; ++lane) tile_frame_store(t, fr[lane], b.tile, lane);
+    if (c + 1 < s.nt) {  // the next tile's interior is read NOW; other tiles run before it is used
+        const Tile tn = make_tile(s, w, c + 1);
+        for (int lane = 0; lane < 32; ++lane) tile_prefetch(s, tn, x, rhs, b.pf[lane], lane);
+    }
     for (int lane = 0; lane < 32; ++lane) west[lane] = 0.f;
     for (int step = 0; step < t.nr + t.nc - 1; ++step)
-        for (int lane = 0; lane < 32; ++lane) tile_step<DIFFUSE>(t, tile, rt, lane, step, a, cc, west[lane]);
-    for (int lane = 0; lane < 32; ++lane) tile_store(s, t, kind, x, tile, lane);
+        for (int lane = 0; lane < 32; ++lane) tile_step<DIFFUSE>(t, b.tile, b.rt, lane, step, a, cc, west[lane]);
+    for (int lane = 0; lane < 32; ++lane) tile_store(s, t, kind, x, b.tile, lane);
 }
 }  // namespace
 
@@ -42,6 +60,7 @@ extern "C" long gs_emul_relax(float* x, const float* rhs, int rows, int cols, in
                               float a, float c, int K, uint64_t order) {
     const Shape s = make_shape(rows, cols, pitch);
     std::vector<unsigned> done((size_t)K * s.nb, 0u);
+    std::vector<Band> bands((size_t)K * s.nb);
     long blocked = 0;
     size_t remaining = (size_t)K * s.nb * s.nt;
     uint64_t rng = order;
@@ -66,9 +85,9 @@ extern "C" long gs_emul_relax(float* x, const float* rhs, int rows, int cols, in
             continue;
         }
         if (diffuse)
-            run_tile<true>(s, w, ct, kind, x, rhs, a, c);
+            run_tile<true>(s, bands[b], w, ct, kind, x, rhs, a, c);
         else
-            run_tile<false>(s, w, ct, kind, x, rhs, a, c);
+            run_tile<false>(s, bands[b], w, ct, kind, x, rhs, a, c);
         ++done[b];
         --remaining;
     }

@@ -70,6 +70,38 @@ def test_solve_host_is_upload_step_download(f2d, sfo, gpu_ok):
         assert s.launch_count() > 0
 
 
+@pytest.mark.parametrize("graph", [True, False], ids=["graph", "eager"])
+@pytest.mark.parametrize("n,kd,kp", [(512, 15, 20), (640, 0, 8), (96, 5, 0)])
+def test_pipelined_solve_host_equals_plain_and_keeps_state(f2d, sfo, gpu_ok, monkeypatch, graph, n, kd, kp):
+    """solve() overlaps uploads, the four parts of the step and downloads (f2d_solve_host, single GPU).  Same
+    bits in u, v as the plain upload -> step -> download path (F2D_HOST_PIPELINE=0) and as the oracle; the
+    device-resident state afterwards equals the host grids, so device-resident stepping can continue from it.
+    512^2 and 640^2 grids are >= 1 MiB and take the page-locking path (cudaHostRegister)."""
+    f = rng_fields(n, 4300 + n)
+    want = sfo.steps(f[0], f[3], DIFFUSION_RATE, f[1], f[2], f[4], f[5], VISCOSITY, DT, kd, kp, nsteps=2)
+    results = {}
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("F2D_HOST_PIPELINE", pipe)
+        hd, hu, hv = f[0].copy(), f[1].copy(), f[2].copy()
+        with f2d.FluidSolverB200(n, n, diffuse_iters=kd, project_iters=kp, divide_mode=DIV_F64, use_graph=graph) as s:
+            for _ in range(2):
+                s.solve(hd, f[3], DIFFUSION_RATE, hu, hv, f[4], f[5], VISCOSITY, DT)
+            sd_, su_, sv_ = s.download()
+            assert_bitwise(su_, hu, "device state u == host u (pipeline=%s)" % pipe)
+            assert_bitwise(sv_, hv, "device state v == host v (pipeline=%s)" % pipe)
+            assert_bitwise(sd_, hd, "device state d == host d (pipeline=%s)" % pipe)
+            # and the device-resident extension continues from there
+            s.set_sources(f[3], f[4], f[5])
+            s.step(DIFFUSION_RATE, VISCOSITY, DT, 1)
+            s.sync()
+            results[pipe] = (hd, hu, hv) + s.download()
+    for k in (1, 2, 4, 5):
+        assert_bitwise(results["1"][k], results["0"][k], "pipelined vs plain, field %d" % k)
+    assert_bitwise(results["1"][1], want[1], "u vs oracle")
+    assert_bitwise(results["1"][2], want[2], "v vs oracle")
+    assert_close(results["1"][0], want[0], "d vs oracle", rel_l2=2 * D_REL_L2, max_abs_rel=2 * D_MAX_ABS)
+
+
 def test_graph_replay_equals_eager(f2d, gpu_ok):
     n = 192
     f = rng_fields(n, 43)
