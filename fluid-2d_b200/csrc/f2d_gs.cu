@@ -31,19 +31,22 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// lane 0: block until *flag >= need.  Bounded: a wait that never ends (a scheduling assumption broken) raises
-// *err and returns, and every other wait then returns at once, so the launch always terminates.
-__device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned need, int* err) {
-    unsigned v = ld_acquire(flag);
+// The whole warp, convergently: block until *flag >= need.  Every lane reads the same word (one transaction) and
+// takes lane 0's value, so control flow stays warp-uniform -- a poll loop run by lane 0 alone leaves the warp split
+// in two for the rest of the tile (measured: every later __syncwarp took the divergent slow path and the step loop
+// issued twice, 46k instead of 6k cycles per tile).  Bounded: a wait that never ends (a scheduling assumption
+// broken) raises *err and returns, and every other wait then returns at once, so the launch always terminates.
+__device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned need, int* err, int lane) {
+    unsigned v = __shfl_sync(0xffffffffu, ld_acquire(flag), 0);
     unsigned spins = 0, ns = 32;
     while (v < need) {
         __nanosleep(ns);
         if (ns < 256) ns *= 2;
-        v = ld_acquire(flag);
+        v = __shfl_sync(0xffffffffu, ld_acquire(flag), 0);
         if ((++spins & 255u) == 0u) {
-            if (*reinterpret_cast<volatile int*>(err)) break;
+            if (__shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(err), 0)) break;
             if (spins >= kSpinLimit) {
-                atomicExch(err, 1);
+                if (lane == 0) atomicExch(err, 1);
                 break;
             }
         }
@@ -57,7 +60,7 @@ __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned
 // LOWER ticket, i.e. to a warp that is already running or finished: the wavefront cannot deadlock however many
 // warps the grid has and however few are resident.
 template <bool DIFFUSE>
-__global__ void __launch_bounds__(kGsWarps * 32) k_gs_relax(GsBatch b) {
+__global__ void __launch_bounds__(kGsWarps * 32, 4) k_gs_relax(GsBatch b) {
     __shared__ float smem[kGsWarps][gs::kTileFloats + gs::kRhsFloats];
     const int lane = threadIdx.x & 31;
     float* tile = smem[threadIdx.x >> 5];
@@ -81,13 +84,12 @@ __global__ void __launch_bounds__(kGsWarps * 32) k_gs_relax(GsBatch b) {
 
     float pf[gs::kPf];  // the next tile's interior + right-hand side, in flight while the current tile computes
     for (int c = 0; c < s.nt; ++c) {
-        if (lane == 0) {
-            const gs::Deps d = gs::tile_deps(s, k, w, c);
+        {
+            const gs::Deps d = gs::tile_deps(s, k, w, c);  // warp-uniform
 #pragma unroll
             for (int i = 0; i < 3; ++i)
-                if (i < d.n && seen[i] < d.need[i]) seen[i] = wait_at_least(done + d.idx[i], d.need[i], b.err);
+                if (i < d.n && seen[i] < d.need[i]) seen[i] = wait_at_least(done + d.idx[i], d.need[i], b.err, lane);
         }
-        __syncwarp();
         const gs::Tile t = gs::make_tile(s, w, c);
         if (c == 0) gs::tile_prefetch(s, t, x, rhs, pf, lane);  // nothing was prefetched for the band's first tile
         const gs::Frame fr = gs::tile_frame_load(s, t, x, tile, lane, c == 0);
@@ -103,8 +105,7 @@ __global__ void __launch_bounds__(kGsWarps * 32) k_gs_relax(GsBatch b) {
             __syncwarp();
         }
         gs::tile_store(s, t, kind, x, tile, lane);
-        __threadfence();
-        __syncwarp();
+        __syncwarp();  // orders every lane's stores before lane 0's release (fence + store), cumulatively
         if (lane == 0) st_release(done + (size_t)k * s.nb + w, (unsigned)(c + 1));
     }
 }

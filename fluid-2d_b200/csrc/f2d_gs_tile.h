@@ -207,15 +207,20 @@ F2D_HD void tile_frame_store(const Tile& t, const Frame& f, float* tile, int lan
 // (north: lane l-1 at step t-1) or that are still old (south, east), so lanes never conflict within a step.
 template <bool DIFFUSE>
 F2D_HD void tile_step(const Tile& t, float* tile, const float* rt, int lane, int step, float a, float c, float& west) {
+    // branch-free: a lane without a cell this step evaluates a valid dummy cell and drops the result, so the warp
+    // never diverges inside the step loop (a diverged warp pays for every __syncwarp and issues the loop twice)
     const int q = step - lane;
-    if (lane >= t.nr || q < 0 || q >= t.nc) return;
-    float* cell = tile + (lane + 1) * kTP + (q + 1);
-    const float n = cell[-kTP], s = cell[kTP], e = cell[1];
-    const float w = (q == 0) ? cell[-1] : west;
-    const float r = rt[lane * kTileCols + q];
+    const bool on = (lane < t.nr) && (q >= 0) && (q < t.nc);
+    const int ql = on ? q : 0, ll = on ? lane : 0;
+    float* cell = tile + (ll + 1) * kTP + (ql + 1);
+    const float n = cell[-kTP], s = cell[kTP], e = cell[1], wl = cell[-1];
+    const float w = (ql == 0) ? wl : west;
+    const float r = rt[ll * kTileCols + ql];
     const float v = DIFFUSE ? diffuse_cell(n, s, w, e, r, a, c) : pressure_cell(n, s, w, e, r);
-    *cell = v;
-    west = v;
+    if (on) {
+        *cell = v;
+        west = v;
+    }
 }
 
 F2D_HD float signed_copy(float v, bool negate) { return negate ? -v : v; }
