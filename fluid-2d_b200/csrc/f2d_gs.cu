@@ -16,15 +16,34 @@
 #include "f2d_gs_tile.h"
 #include "f2d_kernels.cuh"
 
+#ifdef F2D_GS_TIMING
+// Profiling build only (tools/gs_timing.py): cycles per phase of a tile, summed over all warps.
+__device__ unsigned long long g_gs_cycles[8];
+#define GS_T(var) const long long var = clock64()
+#define GS_ACC(i, a, b) \
+    if (lane == 0 && c > 0) atomicAdd(&g_gs_cycles[i], (unsigned long long)((b) - (a)))
+extern "C" __attribute__((visibility("default"))) int f2d_debug_gs_cycles(unsigned long long* out8, int reset) {
+    if (cudaMemcpyFromSymbol(out8, g_gs_cycles, sizeof(g_gs_cycles)) != cudaSuccess) return 1;
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (cudaMemcpyToSymbol(g_gs_cycles, z, sizeof(z)) != cudaSuccess) return 1;
+    }
+    return 0;
+}
+#else
+#define GS_T(var)
+#define GS_ACC(i, a, b)
+#endif
+
 namespace f2d {
 
 namespace {
 constexpr int kGsWarps = 4;
 constexpr unsigned kSpinLimit = 1u << 24;  // polls before a wait gives up and raises the error flag (seconds)
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
     unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
@@ -37,12 +56,13 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 // issued twice, 46k instead of 6k cycles per tile).  Bounded: a wait that never ends (a scheduling assumption
 // broken) raises *err and returns, and every other wait then returns at once, so the launch always terminates.
 __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned need, int* err, int lane) {
-    unsigned v = __shfl_sync(0xffffffffu, ld_acquire(flag), 0);
+    // polls are relaxed loads (served by L2, no L1 invalidation per poll); one acquire fence once the value is in
+    unsigned v = __shfl_sync(0xffffffffu, ld_relaxed(flag), 0);
     unsigned spins = 0, ns = 32;
     while (v < need) {
         __nanosleep(ns);
         if (ns < 256) ns *= 2;
-        v = __shfl_sync(0xffffffffu, ld_acquire(flag), 0);
+        v = __shfl_sync(0xffffffffu, ld_relaxed(flag), 0);
         if ((++spins & 255u) == 0u) {
             if (__shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(err), 0)) break;
             if (spins >= kSpinLimit) {
@@ -51,6 +71,7 @@ __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned
             }
         }
     }
+    __threadfence();  // acquire: the tile data behind the counter is read after this point
     return v;
 }
 }  // namespace
@@ -83,30 +104,51 @@ __global__ void __launch_bounds__(kGsWarps * 32, 4) k_gs_relax(GsBatch b) {
     unsigned seen[3] = {0u, 0u, 0u};  // last value read from each dependency's counter (they only grow)
 
     float pf[gs::kPf];  // the next tile's interior + right-hand side, in flight while the current tile computes
-    for (int c = 0; c < s.nt; ++c) {
+    // c = -1 is a lead-in that only waits for tile 0's neighbours and requests tile 0; tile c then commits what
+    // was requested one iteration earlier, requests tile c + 1 and computes (one request site, one commit site)
+    for (int c = -1; c < s.nt; ++c) {
+        GS_T(t0);
         {
-            const gs::Deps d = gs::tile_deps(s, k, w, c);  // warp-uniform
+            const gs::Deps d = gs::tile_deps(s, k, w, c < 0 ? 0 : c);  // warp-uniform
 #pragma unroll
             for (int i = 0; i < 3; ++i)
                 if (i < d.n && seen[i] < d.need[i]) seen[i] = wait_at_least(done + d.idx[i], d.need[i], b.err, lane);
         }
-        const gs::Tile t = gs::make_tile(s, w, c);
-        if (c == 0) gs::tile_prefetch(s, t, x, rhs, pf, lane);  // nothing was prefetched for the band's first tile
-        const gs::Frame fr = gs::tile_frame_load(s, t, x, tile, lane, c == 0);
-        __syncwarp();  // every lane has read the previous tile's last column
-        gs::tile_commit(t, pf, tile, rt, lane);
-        gs::tile_frame_store(t, fr, tile, lane);
-        __syncwarp();
-        if (c + 1 < s.nt) gs::tile_prefetch(s, gs::make_tile(s, w, c + 1), x, rhs, pf, lane);
-        float west = 0.f;
-        const int nsteps = t.nr + t.nc - 1;
-        for (int step = 0; step < nsteps; ++step) {
-            gs::tile_step<DIFFUSE>(t, tile, rt, lane, step, a, cdiv, west);
+        GS_T(t1);
+        gs::Tile t = gs::make_tile(s, w, c < 0 ? 0 : c);
+        if (c >= 0) {
+            const gs::Frame fr = gs::tile_frame_load(s, t, x, tile, lane, c == 0);
+            __syncwarp();  // every lane has read the previous tile's last column
+            gs::tile_commit(t, pf, tile, rt, lane);
+            gs::tile_frame_store(t, fr, tile, lane);
             __syncwarp();
         }
+        GS_T(t2);
+        if (c + 1 < s.nt) gs::tile_prefetch(s, gs::make_tile(s, w, c + 1), x, rhs, pf, lane);
+        if (c < 0) continue;
+        GS_T(t3);
+        gs::StepRegs g;
+        gs::tile_step_init(t, tile, rt, lane, g);
+        float north = 0.f;
+        const int nsteps = t.nr + t.nc - 1;
+        for (int step = 0; step < nsteps; ++step) {
+            const float v = gs::tile_step<DIFFUSE>(t, tile, rt, lane, step, a, cdiv, g, north);
+            north = __shfl_up_sync(0xffffffffu, v, 1);  // lane l's north neighbour of the next step
+            __syncwarp();
+        }
+        GS_T(t4);
         gs::tile_store(s, t, kind, x, tile, lane);
         __syncwarp();  // orders every lane's stores before lane 0's release (fence + store), cumulatively
+        GS_T(t5);
         if (lane == 0) st_release(done + (size_t)k * s.nb + w, (unsigned)(c + 1));
+        GS_T(t6);
+        GS_ACC(0, t0, t1);
+        GS_ACC(1, t1, t2);
+        GS_ACC(2, t2, t3);
+        GS_ACC(3, t3, t4);
+        GS_ACC(4, t4, t5);
+        GS_ACC(5, t5, t6);
+        GS_ACC(6, 0, 1);
     }
 }
 

@@ -142,14 +142,19 @@ F2D_HD float pressure_cell(float n, float s, float w, float e, float dv) {
 constexpr int kPf = 2 * kBand;  // prefetch registers per lane
 
 F2D_HD void tile_prefetch(const Shape& s, const Tile& t, const float* x, const float* rhs, float* pf, int lane) {
+    // one pointer per array, advanced by the pitch: the address of each of the 64 loads costs one add
     const size_t o = (size_t)t.i0 * s.pitch + t.j0 + lane;
+    const float* px = x + o;
+    const float* pr = rhs + o;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int r = 0; r < kBand; ++r) {
         const bool ok = (r < t.nr) && (lane < t.nc);
-        pf[r] = ok ? ld_iter(x + o + (size_t)r * s.pitch) : 0.f;
-        pf[kBand + r] = ok ? ld_rhs(rhs + o + (size_t)r * s.pitch) : 0.f;
+        pf[r] = ok ? ld_iter(px) : 0.f;
+        pf[kBand + r] = ok ? ld_rhs(pr) : 0.f;
+        px += s.pitch;
+        pr += s.pitch;
     }
 }
 
@@ -176,13 +181,16 @@ F2D_HD Frame tile_frame_load(const Shape& s, const Tile& t, const float* x, cons
 
 F2D_HD void tile_commit(const Tile& t, const float* pf, float* tile, float* rt, int lane) {
     if (lane >= t.nc) return;
+    float* tc = tile + kTP + lane + 1;
+    float* rc = rt + lane;
+    const bool full = (t.nr == kBand);
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int r = 0; r < kBand; ++r)
-        if (r < t.nr) {
-            tile[(r + 1) * kTP + lane + 1] = pf[r];
-            rt[r * kTileCols + lane] = pf[kBand + r];
+        if (full || r < t.nr) {
+            tc[r * kTP] = pf[r];
+            rc[r * kTileCols] = pf[kBand + r];
         }
 }
 
@@ -202,25 +210,59 @@ F2D_HD void tile_frame_store(const Tile& t, const Frame& f, float* tile, int lan
     }
 }
 
-// Phase 2, step t = 0 .. nr + nc - 2: lane l updates cell (row l, column t - l) of the tile.  `west` carries the
-// lane's previous result (the new west neighbour).  A step only reads cells that were written in EARLIER steps
-// (north: lane l-1 at step t-1) or that are still old (south, east), so lanes never conflict within a step.
+// Phase 2, step t = 0 .. nr + nc - 2: lane l updates cell (row l, column t - l) of the tile.  The step is a
+// dependent chain (north comes from lane l-1's previous step, west from the lane's own), so everything that is
+// NOT on the chain is taken off it: the old south / east values and the right-hand side of step t+1 are fetched
+// from shared memory during step t (they are overwritten no earlier than step t+2), the lane's previous result
+// stays in a register (west) and the north value travels by warp shuffle (the caller passes lane l-1's previous
+// result in `north`; lane 0 reads the frame row instead).  The store of the result to shared memory (for the
+// write-back and for the next tile's left column) is off the chain as well.
+struct StepRegs {
+    float west;           // the lane's previous result; initially the frame column left of its row
+    float s, e, r, top;   // operands of the coming step: old south, old east, right-hand side, frame row above lane 0
+};
+
+F2D_HD int step_column(const Tile& t, int lane, int step) {  // the lane's column at `step`, clamped into the tile
+    int q = step - lane;
+    if (q < 0) q = 0;
+    if (q > t.nc - 1) q = t.nc - 1;
+    return q;
+}
+
+F2D_HD void step_fetch(const Tile& t, const float* tile, const float* rt, int lane, int step, StepRegs& g) {
+    const int ll = (lane < t.nr) ? lane : 0, q = step_column(t, lane, step);
+    const float* cell = tile + (ll + 1) * kTP + (q + 1);
+    g.s = cell[kTP];
+    g.e = cell[1];
+    g.top = tile[q + 1];
+    g.r = rt[ll * kTileCols + q];
+}
+
+F2D_HD void tile_step_init(const Tile& t, const float* tile, const float* rt, int lane, StepRegs& g) {
+    const int ll = (lane < t.nr) ? lane : 0;
+    g.west = tile[(ll + 1) * kTP];
+    step_fetch(t, tile, rt, lane, 0, g);
+}
+
+// returns the lane's result of this step (junk if it has no cell this step)
 template <bool DIFFUSE>
-F2D_HD void tile_step(const Tile& t, float* tile, const float* rt, int lane, int step, float a, float c, float& west) {
-    // branch-free: a lane without a cell this step evaluates a valid dummy cell and drops the result, so the warp
-    // never diverges inside the step loop (a diverged warp pays for every __syncwarp and issues the loop twice)
+F2D_HD float tile_step(const Tile& t, float* tile, const float* rt, int lane, int step, float a, float c, StepRegs& g,
+                       float north) {
     const int q = step - lane;
     const bool on = (lane < t.nr) && (q >= 0) && (q < t.nc);
-    const int ql = on ? q : 0, ll = on ? lane : 0;
-    float* cell = tile + (ll + 1) * kTP + (ql + 1);
-    const float n = cell[-kTP], s = cell[kTP], e = cell[1], wl = cell[-1];
-    const float w = (ql == 0) ? wl : west;
-    const float r = rt[ll * kTileCols + ql];
-    const float v = DIFFUSE ? diffuse_cell(n, s, w, e, r, a, c) : pressure_cell(n, s, w, e, r);
+    StepRegs nx;  // operands of step + 1, requested before this step's arithmetic so that their latency hides behind it
+    step_fetch(t, tile, rt, lane, step + 1, nx);
+    const float n = (lane == 0) ? g.top : north;
+    const float v = DIFFUSE ? diffuse_cell(n, g.s, g.west, g.e, g.r, a, c) : pressure_cell(n, g.s, g.west, g.e, g.r);
     if (on) {
-        *cell = v;
-        west = v;
+        tile[(lane + 1) * kTP + (q + 1)] = v;
+        g.west = v;
     }
+    g.s = nx.s;
+    g.e = nx.e;
+    g.r = nx.r;
+    g.top = nx.top;
+    return v;
 }
 
 F2D_HD float signed_copy(float v, bool negate) { return negate ? -v : v; }
@@ -229,10 +271,16 @@ F2D_HD float signed_copy(float v, bool negate) { return negate ? -v : v; }
 F2D_HD void tile_store(const Shape& s, const Tile& t, int kind, float* x, const float* tile, int lane) {
     const bool neg_rows = (kind == kBndOppositeVertical);    // top / bottom rows negate (v)
     const bool neg_cols = (kind == kBndOppositeHorizontal);  // left / right columns negate (u)
-    float* xr = x + (size_t)t.i0 * s.pitch + t.j0;
-    for (int r = 0; r < t.nr; ++r) {
-        if (lane < t.nc) xr[lane] = tile[(r + 1) * kTP + lane + 1];
-        xr += s.pitch;
+    float* xr = x + (size_t)t.i0 * s.pitch + t.j0 + lane;
+    const float* tc = tile + kTP + lane + 1;
+    if (lane < t.nc) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = 0; r < kBand; ++r) {
+            if (r < t.nr) *xr = tc[r * kTP];
+            xr += s.pitch;
+        }
     }
     if (lane < t.nc) {
         if (t.i0 == 1) x[t.j0 + lane] = signed_copy(tile[1 * kTP + lane + 1], neg_rows);

@@ -34,7 +34,6 @@ struct Band {
 
 template <bool DIFFUSE>
 void run_tile(const Shape& s, Band& b, int w, int c, int kind, float* x, const float* rhs, float a, float cc) {
-    float west[32];
     Frame fr[32];
     const Tile t = make_tile(s, w, c);
     if (c == 0)  // the first tile has nothing prefetched: fetch now (after the wait)
@@ -46,9 +45,16 @@ void run_tile(const Shape& s, Band& b, int w, int c, int kind, float* x, const f
         const Tile tn = make_tile(s, w, c + 1);
         for (int lane = 0; lane < 32; ++lane) tile_prefetch(s, tn, x, rhs, b.pf[lane], lane);
     }
-    for (int lane = 0; lane < 32; ++lane) west[lane] = 0.f;
-    for (int step = 0; step < t.nr + t.nc - 1; ++step)
-        for (int lane = 0; lane < 32; ++lane) tile_step<DIFFUSE>(t, b.tile, b.rt, lane, step, a, cc, west[lane]);
+    StepRegs g[32];
+    float north[32], v[32];
+    for (int lane = 0; lane < 32; ++lane) {
+        tile_step_init(t, b.tile, b.rt, lane, g[lane]);
+        north[lane] = 0.f;
+    }
+    for (int step = 0; step < t.nr + t.nc - 1; ++step) {
+        for (int lane = 0; lane < 32; ++lane) v[lane] = tile_step<DIFFUSE>(t, b.tile, b.rt, lane, step, a, cc, g[lane], north[lane]);
+        for (int lane = 0; lane < 32; ++lane) north[lane] = lane ? v[lane - 1] : 0.f;  // __shfl_up_sync(v, 1)
+    }
     for (int lane = 0; lane < 32; ++lane) tile_store(s, t, kind, x, b.tile, lane);
 }
 }  // namespace
