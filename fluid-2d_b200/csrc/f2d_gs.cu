@@ -58,10 +58,10 @@ __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
 __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned need, int* err, int lane) {
     // polls are relaxed loads (served by L2, no L1 invalidation per poll); one acquire fence once the value is in
     unsigned v = __shfl_sync(0xffffffffu, ld_relaxed(flag), 0);
-    unsigned spins = 0, ns = 32;
+    unsigned spins = 0, ns = 0;
     while (v < need) {
-        __nanosleep(ns);
-        if (ns < 256) ns *= 2;
+        if (ns) __nanosleep(ns);  // a neighbour that is one tile behind arrives within a few polls: spin first, then back off
+        if (spins >= 8 && ns < 256) ns = ns ? 2 * ns : 32;
         v = __shfl_sync(0xffffffffu, ld_relaxed(flag), 0);
         if ((++spins & 255u) == 0u) {
             if (__shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(err), 0)) break;
@@ -71,7 +71,7 @@ __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned
             }
         }
     }
-    __threadfence();  // acquire: the tile data behind the counter is read after this point
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");  // acquire: the tile data behind the counter is read after this point
     return v;
 }
 }  // namespace
@@ -82,9 +82,9 @@ __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned
 // warps the grid has and however few are resident.
 template <bool DIFFUSE>
 __global__ void __launch_bounds__(kGsWarps * 32, 4) k_gs_relax(GsBatch b) {
-    __shared__ float smem[kGsWarps][gs::kTileFloats + gs::kRhsFloats];
+    __shared__ float smem[kGsWarps][gs::kWarpFloats];
     const int lane = threadIdx.x & 31;
-    float* tile = smem[threadIdx.x >> 5];
+    float* tile = smem[threadIdx.x >> 5] + gs::kPad;
     float* rt = tile + gs::kTileFloats;
 
     unsigned ticket = 0;
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kGsWarps * 32, 4) k_gs_relax(GsBatch b) {
         float north = 0.f;
         const int nsteps = t.nr + t.nc - 1;
         for (int step = 0; step < nsteps; ++step) {
-            const float v = gs::tile_step<DIFFUSE>(t, tile, rt, lane, step, a, cdiv, g, north);
+            const float v = gs::tile_step<DIFFUSE>(t, lane, step, a, cdiv, g, north);
             north = __shfl_up_sync(0xffffffffu, v, 1);  // lane l's north neighbour of the next step
             __syncwarp();
         }

@@ -39,6 +39,11 @@ constexpr int kTileCols = 32;                      // interior columns per tile
 constexpr int kTP = kTileCols + 2;                 // pitch of the value tile; kTP - 1 is odd: skewed accesses hit 32 banks
 constexpr int kTileFloats = (kBand + 2) * kTP;     // value tile with a one-cell frame
 constexpr int kRhsFloats = kBand * kTileCols;      // right-hand side tile (pitch kTileCols: 31 * l + t, conflict-free)
+// One warp's on-chip block: [kPad slack][value tile][rhs tile][kPad slack], contiguous.  The step loop addresses its
+// operands with unclamped column offsets; a lane whose column is outside the tile (the skew's ramp-up / ramp-down)
+// then reads up to 31 floats before or after its row.  Those reads are discarded, the slack keeps them in bounds.
+constexpr int kPad = 64;
+constexpr int kWarpFloats = kPad + kTileFloats + kRhsFloats + kPad;
 
 // boundary kinds as in include/f2d.h
 constexpr int kBndContinuous = 0, kBndOppositeHorizontal = 1, kBndOppositeVertical = 2;
@@ -218,50 +223,47 @@ F2D_HD void tile_frame_store(const Tile& t, const Frame& f, float* tile, int lan
 // result in `north`; lane 0 reads the frame row instead).  The store of the result to shared memory (for the
 // write-back and for the next tile's left column) is off the chain as well.
 struct StepRegs {
-    float west;           // the lane's previous result; initially the frame column left of its row
-    float s, e, r, top;   // operands of the coming step: old south, old east, right-hand side, frame row above lane 0
+    float west;          // the lane's previous result; initially the frame column left of its row
+    float s, e, r, top;  // operands of the coming step: old south, old east, right-hand side, frame row above lane 0
+    float* cell;         // the lane's cell of the coming step (unclamped column)
+    const float* rp;     // its right-hand side
+    const float* tp;     // the frame-row cell above that column
 };
 
-F2D_HD int step_column(const Tile& t, int lane, int step) {  // the lane's column at `step`, clamped into the tile
-    int q = step - lane;
-    if (q < 0) q = 0;
-    if (q > t.nc - 1) q = t.nc - 1;
-    return q;
+F2D_HD void step_fetch(StepRegs& g) {
+    g.s = g.cell[kTP];
+    g.e = g.cell[1];
+    g.top = *g.tp;
+    g.r = *g.rp;
 }
 
-F2D_HD void step_fetch(const Tile& t, const float* tile, const float* rt, int lane, int step, StepRegs& g) {
-    const int ll = (lane < t.nr) ? lane : 0, q = step_column(t, lane, step);
-    const float* cell = tile + (ll + 1) * kTP + (q + 1);
-    g.s = cell[kTP];
-    g.e = cell[1];
-    g.top = tile[q + 1];
-    g.r = rt[ll * kTileCols + q];
-}
-
-F2D_HD void tile_step_init(const Tile& t, const float* tile, const float* rt, int lane, StepRegs& g) {
-    const int ll = (lane < t.nr) ? lane : 0;
+// `tile` and `rt` must be the two halves of a warp block (kPad floats of slack on either side).
+F2D_HD void tile_step_init(const Tile& t, float* tile, const float* rt, int lane, StepRegs& g) {
+    const int ll = (lane < t.nr) ? lane : 0;  // rows beyond the band shadow row 0 and never store
     g.west = tile[(ll + 1) * kTP];
-    step_fetch(t, tile, rt, lane, 0, g);
+    g.cell = tile + (ll + 1) * kTP + (1 - lane);  // column q = step - lane, step = 0
+    g.rp = rt + ll * kTileCols - lane;
+    g.tp = tile + (1 - lane);
+    step_fetch(g);
 }
 
 // returns the lane's result of this step (junk if it has no cell this step)
 template <bool DIFFUSE>
-F2D_HD float tile_step(const Tile& t, float* tile, const float* rt, int lane, int step, float a, float c, StepRegs& g,
-                       float north) {
-    const int q = step - lane;
-    const bool on = (lane < t.nr) && (q >= 0) && (q < t.nc);
-    StepRegs nx;  // operands of step + 1, requested before this step's arithmetic so that their latency hides behind it
-    step_fetch(t, tile, rt, lane, step + 1, nx);
-    const float n = (lane == 0) ? g.top : north;
-    const float v = DIFFUSE ? diffuse_cell(n, g.s, g.west, g.e, g.r, a, c) : pressure_cell(n, g.s, g.west, g.e, g.r);
+F2D_HD float tile_step(const Tile& t, int lane, int step, float a, float c, StepRegs& g, float north) {
+    const bool on = (lane < t.nr) && ((unsigned)(step - lane) < (unsigned)t.nc);
+    float* const here = g.cell;
+    const float cs = g.s, ce = g.e, cr = g.r, ct = g.top;
+    // operands of step + 1, requested before this step's arithmetic so that their latency hides behind it
+    g.cell = here + 1;
+    g.rp += 1;
+    g.tp += 1;
+    step_fetch(g);
+    const float n = (lane == 0) ? ct : north;
+    const float v = DIFFUSE ? diffuse_cell(n, cs, g.west, ce, cr, a, c) : pressure_cell(n, cs, g.west, ce, cr);
     if (on) {
-        tile[(lane + 1) * kTP + (q + 1)] = v;
+        *here = v;
         g.west = v;
     }
-    g.s = nx.s;
-    g.e = nx.e;
-    g.r = nx.r;
-    g.top = nx.top;
     return v;
 }
 

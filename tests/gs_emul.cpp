@@ -24,12 +24,14 @@ uint64_t next_rand(uint64_t& s) {
 
 // on-chip state of one warp = one (sweep, band): shared-memory tiles and the prefetch registers of its 32 lanes
 struct Band {
-    float tile[kTileFloats], rt[kRhsFloats];
+    float block[kWarpFloats];  // the warp block of the kernel: slack, value tile, rhs tile, slack
+    float* tile;
+    float* rt;
     float pf[32][kPf];
-    Band() {
-        for (int i = 0; i < kTileFloats; ++i) tile[i] = -12345.0f;  // poison: an unloaded cell must never be used
-        for (int i = 0; i < kRhsFloats; ++i) rt[i] = -54321.0f;
+    Band() : tile(block + kPad), rt(block + kPad + kTileFloats) {
+        for (int i = 0; i < kWarpFloats; ++i) block[i] = -12345.0f;  // poison: an unloaded cell must never be used
     }
+    Band(const Band&) : Band() {}
 };
 
 template <bool DIFFUSE>
@@ -52,7 +54,7 @@ void run_tile(const Shape& s, Band& b, int w, int c, int kind, float* x, const f
         north[lane] = 0.f;
     }
     for (int step = 0; step < t.nr + t.nc - 1; ++step) {
-        for (int lane = 0; lane < 32; ++lane) v[lane] = tile_step<DIFFUSE>(t, b.tile, b.rt, lane, step, a, cc, g[lane], north[lane]);
+        for (int lane = 0; lane < 32; ++lane) v[lane] = tile_step<DIFFUSE>(t, lane, step, a, cc, g[lane], north[lane]);
         for (int lane = 0; lane < 32; ++lane) north[lane] = lane ? v[lane - 1] : 0.f;  // __shfl_up_sync(v, 1)
     }
     for (int lane = 0; lane < 32; ++lane) tile_store(s, t, kind, x, b.tile, lane);
