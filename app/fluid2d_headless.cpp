@@ -4,7 +4,7 @@
 // The reference's parse_simulation_config ignores argv ("TODO", src/app.cpp:27-36); this one parses it.
 //
 //   fluid2d_headless [--size N | --width W --height H] [--steps S] [--dt 0.02] [--diffusion 0.5]
-//                    [--viscosity 1e-6] [--kd 15] [--kp 20] [--no-smooth] [--exact-divide]
+//                    [--viscosity 1e-6] [--kd 15] [--kp 20] [--no-smooth] [--exact-divide] [--solver b200|b200-cpu-exact]
 //                    [--load prefix] [--dump prefix] [--dump-every K] [--ppm file.ppm] [--quiet]
 //   --load/--dump use prefix_{density,u,v}.npy (include/f2d_npy.hpp)
 #include <cmath>
@@ -42,6 +42,12 @@ bool parse(int argc, char** argv, args& a) {
         else if (is("--kp")) { if (!(v = val())) return false; a.cfg.solver_options.project_iterations = std::atoi(v); }
         else if (is("--no-smooth")) a.cfg.solver_options.smooth = false;
         else if (is("--exact-divide")) a.cfg.solver_options.exact_divide = true;
+        else if (is("--solver")) {  // the switch of src/simulation.cpp:17-26
+            if (!(v = val())) return false;
+            if (std::strcmp(v, "b200") == 0) a.cfg.solver = solver_type::b200;
+            else if (std::strcmp(v, "b200-cpu-exact") == 0) a.cfg.solver = solver_type::b200_cpu_exact;
+            else return false;
+        }
         else if (is("--load")) { if (!(v = val())) return false; a.load = v; }
         else if (is("--dump")) { if (!(v = val())) return false; a.dump = v; }
         else if (is("--ppm")) { if (!(v = val())) return false; a.ppm = v; }
@@ -73,7 +79,7 @@ int main(int argc, char** argv) {
     args a;
     if (!parse(argc, argv, a)) {
         std::fprintf(stderr, "usage: %s [--size N] [--steps S] [--dt s] [--diffusion r] [--viscosity v] [--kd K] [--kp K]\n"
-                             "          [--no-smooth] [--exact-divide] [--load prefix] [--dump prefix] [--dump-every K] [--quiet]\n", argv[0]);
+                             "          [--no-smooth] [--exact-divide] [--solver b200|b200-cpu-exact] [--load prefix] [--dump prefix] [--dump-every K] [--quiet]\n", argv[0]);
         return 64;
     }
     try {

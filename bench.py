@@ -212,6 +212,21 @@ def run_single_gpu(args, workload):
     e2e_value = cells * e2e_steps / e2e_s
     solver.close()
 
+    # ---- the fluid_solver_cpu-compatible mode (F2D_SEM_CPU, bit-identical to the reference arm's solver) on the
+    #      reference arm's own sample (1024^2, the workload's K): what "the same bits, on the GPU" costs
+    n_x = 1024
+    fx = canonical(n_x)
+    with f2d.FluidSolverB200.cpu_compatible(n_x, n_x, iters=kd, device=0) as sx:
+        sx.upload(*fx[:3])
+        sx.set_sources(*fx[3:])
+        sx.step(DIFFUSION_RATE, VISCOSITY, DT, 2)
+        sx.sync()
+        x_ms = sx.step_timed(DIFFUSION_RATE, VISCOSITY, DT, 5) / 5
+        sx.sync()
+    exact_mode = {"value": n_x * n_x / (x_ms * 1e-3), "unit": UNIT, "ms_per_step": x_ms,
+                  "workload": "%dx%d grid, K=%d Gauss-Seidel sweeps, fluid_solver_cpu arithmetic (F2D_SEM_CPU), device-resident" % (n_x, n_x, kd),
+                  "parity": "bit-identical to fluid_solver_cpu::solve (tests/test_gpu_cpu_semantics.py)"}
+
     # ---- CPU baseline on this box's host cores: bounded sample (one step of a 2048^2 grid)
     run, kind = cpu_reference_solver()
     n_s = 2048 if kd >= 40 else 4096
@@ -248,7 +263,8 @@ def run_single_gpu(args, workload):
                                    % (n_s, n_s, kd, os.cpu_count())},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(6 * 4 * cells),
                 "d2h_bytes_per_step": int(3 * 4 * cells), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                "api": "FluidSolverB200.solve -> f2d_solve_host (pinned host grids)"},
+                "api": "FluidSolverB200.solve -> f2d_solve_host (pinned host grids; uploads, step parts and downloads overlapped)"},
+        "cpu_exact_mode": exact_mode,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -17,7 +17,10 @@
 #include "fluid_solver.hpp"
 #include "fluid_solver_b200.hpp"
 
-enum class solver_type { b200 };  // the reference's enumerators are { gpu, cpu }; see INTEGRATION.md for the merged switch
+// The reference's enumerators are { gpu, cpu } (src/simulation.hpp:14); see INTEGRATION.md for the merged switch.
+//   b200            the arithmetic of fluid_solver_gpu (the reference's default solver, src/app.cpp:32)
+//   b200_cpu_exact  the arithmetic of fluid_solver_cpu, bit for bit (F2D_SEM_CPU: Gauss-Seidel, 20 iterations, no smooth)
+enum class solver_type { b200, b200_cpu_exact };
 
 struct simulation_config {
     size_t width = 800;             // src/app.cpp:30-31
@@ -42,6 +45,12 @@ public:
             case solver_type::b200:
                 m_solver = std::make_unique<fluid_solver_b200>(config.height, config.width, config.solver_options);
                 break;
+            case solver_type::b200_cpu_exact: {
+                fluid_solver_b200::options o = fluid_solver_b200::options::cpu_compatible();
+                o.device = config.solver_options.device;
+                m_solver = std::make_unique<fluid_solver_b200>(config.height, config.width, o);
+                break;
+            }
         }
     }
 

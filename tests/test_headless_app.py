@@ -90,3 +90,28 @@ def test_headless_run_matches_oracle(f2d, sfo, gpu_ok, tmp_path):
     r2 = subprocess.run([app, "--size", str(n), "--steps", "0", "--load", prefix, "--dump", prefix + "_b"], capture_output=True, text=True)
     assert r2.returncode == 0, r2.stderr
     assert np.array_equal(np.load(prefix + "_b_u.npy"), gu)
+
+
+@pytest.mark.gpu
+def test_headless_run_cpu_exact_solver_is_bit_identical_to_fluid_solver_cpu(f2d, sfo, gpu_ok, tmp_path):
+    """--solver b200-cpu-exact: the same 8 frames, now with fluid_solver_cpu's arithmetic (src/simulation.cpp:19 would
+    pick fluid_solver_cpu here).  Every field bit-identical to the unmodified fluid_solver_cpu::solve when
+    oracle/_ref/libref_cpu.so travelled to the box, else to the oracle pinned against it."""
+    from oracle import refs
+
+    app = build_app(f2d)
+    n, steps = 96, 8
+    prefix = str(tmp_path / "cpuexact")
+    r = subprocess.run([app, "--size", str(n), "--steps", str(steps), "--solver", "b200-cpu-exact", "--dump", prefix],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = refs.ref_cpu() if refs.have_cpu() else None
+    d, u, v = (np.zeros((n, n), np.float32) for _ in range(3))
+    for s in range(steps):
+        sd, su, sv = scripted_sources(n, s)
+        if ref is not None:
+            d, u, v = ref.solve(d, sd, 0.5, u, v, su, sv, 1e-6, 0.02, 1)
+        else:
+            d, u, v = sfo.steps(d, sd, 0.5, u, v, su, sv, 1e-6, 0.02, 20, 20, smooth=False, sem=sfo.SEM_CPU, nsteps=1)
+    for name, want in (("density", d), ("u", u), ("v", v)):
+        assert_bitwise(np.load(prefix + "_%s.npy" % name), want, name)
