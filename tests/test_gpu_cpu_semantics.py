@@ -139,6 +139,23 @@ def test_reproduces_the_anchors_of_the_unmodified_cpu_solver(f2d, sfo, gpu_ok, s
         assert "%016x" % sfo.fnv1a64(a) == anchors[str(steps)][name]["fnv"], (name, steps)
 
 
+def test_full_size_step_2048(f2d, sfo, gpu_ok):
+    """One fluid_solver_cpu::solve step at 2048^2 on the canonical fields (the oracle needs a few seconds for it):
+    64 row bands x 64 column tiles x 20 sweeps x 3 problems in flight, every field bit-identical."""
+    n = 2048
+    d, u, v, sd, su, sv = sfo.canonical_fields(n)
+    with f2d.FluidSolverB200.cpu_compatible(n, n) as s:
+        s.upload(d, u, v)
+        s.set_sources(sd, su, sv)
+        s.step(DIFFUSION_RATE, VISCOSITY, DT, 1)
+        s.sync()
+        gd, gu, gv = s.download()
+    od, ou, ov = sfo.steps(d, sd, DIFFUSION_RATE, u, v, su, sv, VISCOSITY, DT, 20, 20, smooth=False, sem=sfo.SEM_CPU, nsteps=1)
+    assert_bitwise(gu, ou, "u")
+    assert_bitwise(gv, ov, "v")
+    assert_bitwise(gd, od, "d")
+
+
 def test_solve_host_against_live_reference_cpu_solver(f2d, sfo, gpu_ok):
     """fluid_solver::solve through the C ABI on host grids vs the unmodified fluid_solver_cpu::solve
     (oracle/_ref/libref_cpu.so travels to the box; falls back to the pinned oracle when it did not)."""
