@@ -9,7 +9,7 @@
 //                     bands chained through progress counters in global memory;
 //   k_scatter_ordered the density scatter as a gather: every target cell scans the sources that can reach it in
 //                     lexicographic order, so the float additions happen in the CPU's order (no atomics);
-//   k_max_disp        the reach of that scan (largest displacement, in cells);
+//   k_scatter_keys    every source's landing cell and the reach of that scan (largest displacement, in cells);
 //   k_add_sources_nofma, k_advect_velocity_nofma, k_corners_avg.
 // Divergence and gradient subtract have the same operations in both reference solvers
 // (cpp:190-193, :207-211 vs gpu.cu:173-174, :202-203) and reuse the kernels of f2d_kernels_simple.cu.
@@ -60,7 +60,15 @@ __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned
     unsigned v = __shfl_sync(0xffffffffu, ld_relaxed(flag), 0);
     unsigned spins = 0, ns = 0;
     while (v < need) {
-        if (ns) __nanosleep(ns);  // a neighbour that is one tile behind arrives within a few polls: spin first, then back off
+        // a neighbour one tile behind arrives within a few polls: spin, then back off gently.  One that is several
+        // tiles behind (a band that has not reached this column yet, a later sweep waiting for its turn) cannot
+        // arrive sooner than a tile takes (~4 us): sleep accordingly and keep the memory system free for the
+        // warps that are on the wavefront.
+        const unsigned behind = need - v;
+        if (behind > 1u)
+            __nanosleep(behind > 8u ? 16000u : 2000u * (behind - 1u));
+        else if (ns)
+            __nanosleep(ns);
         if (spins >= 8 && ns < 256) ns = ns ? 2 * ns : 32;
         v = __shfl_sync(0xffffffffu, ld_relaxed(flag), 0);
         if ((++spins & 255u) == 0u) {
@@ -245,33 +253,51 @@ void launch_advect_velocity_nofma(const Geom& g, const float* u0, const float* v
 }
 
 // ----------------------------------------------------------------------- advect (ordered scatter)
-// Largest forward displacement max(|dt0*u|, |dt0*v|) over the interior, as the bit pattern of a non-negative
-// float (integer max == float max there; a NaN compares above everything and widens the scan to the grid).
-__global__ void __launch_bounds__(256) k_max_disp(Geom g, const float* __restrict__ u, const float* __restrict__ v, float dt0,
-                                                 unsigned* bits) {
-    unsigned m = 0u;
-    for (int i = 1 + blockIdx.y * 8 + threadIdx.y; i <= g.rows - 2; i += gridDim.y * 8)
-        for (int j = 1 + blockIdx.x * 32 + threadIdx.x; j <= g.cols - 2; j += gridDim.x * 32) {
-            const size_t o = (size_t)i * g.pitch + j;
-            m = max(m, __float_as_uint(fabsf(__fmul_rn(dt0, __ldg(u + o)))));
-            m = max(m, __float_as_uint(fabsf(__fmul_rn(dt0, __ldg(v + o)))));
-        }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
-    if (threadIdx.x == 0 && m) atomicMax(bits, m);
-}
-
 // cpp:127-152 turned inside out.  The reference zeroes the field, then walks the sources (i,j) in lexicographic
 // order and adds four weighted copies of each into the cells around its forward-traced position.  A target cell
 // therefore receives its contributions in lexicographic SOURCE order, and float addition makes that order part of
-// the result.  Here one thread owns one interior target cell and visits, in the same order, every source whose
-// displacement can reach it (|di|, |dj| <= R = ceil(max displacement) + 1), recomputing the source's landing
-// point exactly as the reference does (product rounded, then added) and adding its share if it lands here.
+// the result.  Two passes, no atomics on the data:
+//   k_scatter_keys     one thread per source: the landing cell (i0, j0) as a linear index, or ~0 if the source is
+//                      skipped (cpp:134); also the largest displacement max(|dt0*u|, |dt0*v|) as the bit pattern of
+//                      a non-negative float (integer max == float max there; a NaN compares above everything and
+//                      widens the scan to the whole grid);
+//   k_scatter_ordered  one thread per interior target: visits, in lexicographic order, every source whose
+//                      displacement can reach it (|di|, |dj| <= R = ceil(max displacement) + 1); a source lands
+//                      here iff target - key is one of {0, 1, pitch, pitch + 1}; only then its position is
+//                      recomputed exactly as the reference does (product rounded, then added) and its share added.
 // Edge cells and corners are overwritten by the boundary pass that follows (cpp:176), so only the interior is
 // produced.
+constexpr unsigned kNoKey = 0xffffffffu;
+
+__device__ __forceinline__ bool forward_trace(const Geom& g, int i, int j, float uu, float vv, float dt0, float& x, float& y) {
+    x = __fadd_rn((float)j, __fmul_rn(dt0, uu));
+    y = __fadd_rn((float)i, __fmul_rn(dt0, vv));
+    return !(x < 0.5f || x > (float)g.cols - 1.5f || y < 0.5f || y > (float)g.rows - 1.5f);
+}
+
+__global__ void __launch_bounds__(256) k_scatter_keys(Geom g, const float* __restrict__ u, const float* __restrict__ v, float dt0,
+                                                     unsigned* __restrict__ keys, unsigned* disp_bits) {
+    const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
+    unsigned m = 0u;
+    if (i < g.rows && j < g.cols) {
+        const size_t o = (size_t)i * g.pitch + j;
+        unsigned key = kNoKey;
+        if (i >= 1 && i <= g.rows - 2 && j >= 1 && j <= g.cols - 2) {
+            const float uu = __ldg(u + o), vv = __ldg(v + o);
+            m = max(__float_as_uint(fabsf(__fmul_rn(dt0, uu))), __float_as_uint(fabsf(__fmul_rn(dt0, vv))));
+            float x, y;
+            if (forward_trace(g, i, j, uu, vv, dt0, x, y)) key = (unsigned)(int)y * (unsigned)g.pitch + (unsigned)(int)x;
+        }
+        keys[o] = key;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if (threadIdx.x == 0 && m) atomicMax(disp_bits, m);
+}
+
 __global__ void __launch_bounds__(256) k_scatter_ordered(Geom g, const float* __restrict__ src, const float* __restrict__ u,
-                                                        const float* __restrict__ v, float* __restrict__ out, float dt0,
-                                                        const unsigned* __restrict__ disp_bits) {
+                                                        const float* __restrict__ v, const unsigned* __restrict__ keys,
+                                                        float* __restrict__ out, float dt0, const unsigned* __restrict__ disp_bits) {
     const int tj = 1 + blockIdx.x * 32 + threadIdx.x, ti = 1 + blockIdx.y * 8 + threadIdx.y;
     if (ti > g.rows - 2 || tj > g.cols - 2) return;
     const float md = __uint_as_float(*disp_bits);
@@ -279,34 +305,30 @@ __global__ void __launch_bounds__(256) k_scatter_ordered(Geom g, const float* __
     const int R = (md < (float)far) ? (int)ceilf(md) + 1 : far;  // also catches NaN / inf
     const int ilo = max(1, ti - R), ihi = min(g.rows - 2, ti + R);
     const int jlo = max(1, tj - R), jhi = min(g.cols - 2, tj + R);
-    const float xmax = (float)g.cols - 1.5f, ymax = (float)g.rows - 1.5f;
+    const unsigned P = (unsigned)g.pitch, T = (unsigned)ti * P + (unsigned)tj;
     float acc = 0.f;
     for (int i = ilo; i <= ihi; ++i) {
         const size_t row = (size_t)i * g.pitch;
         for (int j = jlo; j <= jhi; ++j) {
-            const float y = __fadd_rn((float)i, __fmul_rn(dt0, __ldg(v + row + j)));
-            if (y < 0.5f || y > ymax) continue;
-            const int di = ti - (int)y;
-            if ((unsigned)di > 1u) continue;
-            const float x = __fadd_rn((float)j, __fmul_rn(dt0, __ldg(u + row + j)));
-            if (x < 0.5f || x > xmax) continue;
-            const int dj = tj - (int)x;
-            if ((unsigned)dj > 1u) continue;
+            const unsigned d = T - __ldg(keys + row + j);  // kNoKey gives T + 1 >= pitch + 2: never a hit
+            if (d > P + 1u || (d > 1u && d < P)) continue;
+            float x, y;
+            forward_trace(g, i, j, __ldg(u + row + j), __ldg(v + row + j), dt0, x, y);
             const Bilinear b = bilinear_setup(x, y);
-            const float wx = dj ? b.s0 : b.s1, wy = di ? b.s2 : b.s3;
+            const float wx = (d == 1u || d == P + 1u) ? b.s0 : b.s1;  // landed one column left of the target: right-hand weight
+            const float wy = (d >= P) ? b.s2 : b.s3;                  // landed one row above the target: lower weight
             acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wx, wy), __ldg(src + row + j)));
         }
     }
     out[(size_t)ti * g.pitch + tj] = acc;
 }
 
-void launch_scatter_ordered(const Geom& g, const float* src, const float* u, const float* v, float* out, float dt0,
-                            unsigned* disp_bits, cudaStream_t st) {
+void launch_scatter_ordered(const Geom& g, const float* src, const float* u, const float* v, float* out, unsigned* keys,
+                            float dt0, unsigned* disp_bits, cudaStream_t st) {
     cudaMemsetAsync(disp_bits, 0, sizeof(unsigned), st);
     const dim3 bl(32, 8);
-    const dim3 gr_red(min((g.cols + 31) / 32, 64), min((g.rows + 7) / 8, 256));
-    k_max_disp<<<gr_red, bl, 0, st>>>(g, u, v, dt0, disp_bits);
-    k_scatter_ordered<<<dim3((g.cols - 2 + 31) / 32, (g.rows - 2 + 7) / 8), bl, 0, st>>>(g, src, u, v, out, dt0, disp_bits);
+    k_scatter_keys<<<dim3((g.cols + 31) / 32, (g.rows + 7) / 8), bl, 0, st>>>(g, u, v, dt0, keys, disp_bits);
+    k_scatter_ordered<<<dim3((g.cols - 2 + 31) / 32, (g.rows - 2 + 7) / 8), bl, 0, st>>>(g, src, u, v, keys, out, dt0, disp_bits);
 }
 
 }  // namespace f2d

@@ -74,9 +74,10 @@ void launch_corners_avg(const Geom& g, const CornerBatch& b, cudaStream_t st);
 void launch_add_sources_nofma(const Geom& g, const AddSourceBatch& b, float dt, cudaStream_t st);
 void launch_advect_velocity_nofma(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out, float dt0,
                                   cudaStream_t st);
-// density scatter in the CPU solver's summation order; writes the interior of `out` only.  disp_bits: one device word.
-void launch_scatter_ordered(const Geom& g, const float* src, const float* u, const float* v, float* out, float dt0,
-                            unsigned* disp_bits, cudaStream_t st);
+// density scatter in the CPU solver's summation order; writes the interior of `out` only.  keys: one scratch field
+// (rows * pitch words), disp_bits: one device word.  Needs rows * pitch < 2^32 - 2.
+void launch_scatter_ordered(const Geom& g, const float* src, const float* u, const float* v, float* out, unsigned* keys,
+                            float dt0, unsigned* disp_bits, cudaStream_t st);
 
 // ---- peer-to-peer halo exchange (f2d_p2p.cu)
 struct XchgSeg {

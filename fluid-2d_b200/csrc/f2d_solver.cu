@@ -577,10 +577,11 @@ struct f2d_solver {
     // density advect (cpp:127-152 + :176): f <- scatter of f by (u, v) with the boundary pass.  `do_smooth` adds
     // fluid_solver_gpu's density smooth (gpu.cu:314-323); fluid_solver_cpu has none.
     int advect_density_cpu(float* f, const float* u, const float* v, float dt, bool do_smooth) {
-        float* sc = acquire();
-        if (!sc) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-        launch_scatter_ordered(g, f, u, v, sc, dt0_cpu(dt), gs_aux + 1, stream);  // interior of sc
+        float *sc = acquire(), *keys = acquire();
+        if (!sc || !keys) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        launch_scatter_ordered(g, f, u, v, sc, reinterpret_cast<unsigned*>(keys), dt0_cpu(dt), gs_aux + 1, stream);  // interior of sc
         count(2);
+        release(keys);
         launch_smooth_bnd(g, sc, f, do_smooth, stream);  // edges from the scattered interior, out of place
         count();
         release(sc);
@@ -1253,6 +1254,8 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     if (cfg->semantics != F2D_SEM_GPU && cfg->semantics != F2D_SEM_CPU) return fail(F2D_ERR_INVALID, "unknown semantics");
     if (cfg->semantics == F2D_SEM_CPU && (cfg->halo != 0 || cfg->row_offset != 0 || grows != cfg->rows))
         return fail(F2D_ERR_INVALID, "F2D_SEM_CPU runs on one GPU only (the Gauss-Seidel wavefront is not split into slabs)");
+    if (cfg->semantics == F2D_SEM_CPU && (uint64_t)cfg->rows * ((cfg->cols + 31u) / 32u * 32u) >= 0xfffffffeull)
+        return fail(F2D_ERR_INVALID, "F2D_SEM_CPU: grid too large for 32-bit cell indices");
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
