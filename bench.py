@@ -242,6 +242,29 @@ def run_single_gpu(args, workload):
                   "workload": "%dx%d grid, K=%d Gauss-Seidel sweeps, fluid_solver_cpu arithmetic (F2D_SEM_CPU), device-resident" % (n_x, n_x, kd),
                   "parity": "bit-identical to fluid_solver_cpu::solve (tests/test_gpu_cpu_semantics.py)"}
 
+    # ---- strong-scaling base: the N > 1 runs use the 16384^2 grid (configs[3]); its single-GPU time is what their
+    #      values have to be divided by (the headline above is the 4096^2 roofline config, a different workload)
+    scaling_base = None
+    if not args.size and not args.iters and os.environ.get("F2D_BENCH_SCALING_BASE", "1") == "1":
+        try:
+            from bench_multi import canonical_rows
+
+            nb = 16384
+            fb = canonical_rows(nb, 0, nb)
+            with f2d.FluidSolverB200(nb, nb, diffuse_iters=kd, project_iters=kp, device=0) as sb:
+                sb.upload(*fb[:3])
+                sb.set_sources(*fb[3:])
+                del fb
+                sb.step(DIFFUSION_RATE, VISCOSITY, DT, 3)
+                sb.sync()
+                b_ms = sb.step_timed(DIFFUSION_RATE, VISCOSITY, DT, 5) / 5
+                sb.sync()
+            scaling_base = {"workload": "16384x16384 grid, Kd=Kp=%d on ONE GPU (the workload of the N > 1 runs)" % kd,
+                            "value": float(nb) * nb / (b_ms * 1e-3), "unit": UNIT, "ms_per_step": b_ms, "steps": 5,
+                            "note": "strong-scaling efficiency of an N-GPU line = its value / (N * this value)"}
+        except Exception as e:  # e.g. not enough host memory on a small box: the headline does not depend on it
+            scaling_base = {"unavailable": str(e)[:200]}
+
     # ---- CPU baseline on this box's host cores: bounded sample (one step of a 2048^2 grid)
     run, kind = cpu_reference_solver()
     n_s = 2048 if kd >= 40 else 4096
@@ -280,6 +303,7 @@ def run_single_gpu(args, workload):
                 "d2h_bytes_per_step": int(3 * 4 * cells), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                 "api": "FluidSolverB200.solve -> f2d_solve_host (pinned host grids; uploads, step parts and downloads overlapped)"},
         "cpu_exact_mode": exact_mode,
+        "scaling_base": scaling_base,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
