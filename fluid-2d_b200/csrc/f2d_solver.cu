@@ -104,6 +104,7 @@ struct f2d_solver {
     // The new velocity lands in out_u / out_v (pool buffers held for the life of the solver), so that part 3 still
     // finds the pre-step u, v in the state buffers; it is copied into the state after part 3.
     bool host_pipeline = true;  // F2D_HOST_PIPELINE=0: upload everything, one step graph, download (A/B)
+    size_t host_pipeline_min_bytes = 1u << 20;  // smaller fields take the serial order: nothing to hide, 3 extra graph launches (profiles/solve_ab_r01.log)
     cudaStream_t up_stream = nullptr;
     cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_vel = nullptr, ev_fence = nullptr;
     cudaGraphExec_t host_exec[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1364,6 +1365,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
         cudaEventCreateWithFlags(&s->ev_fence, cudaEventDisableTiming) != cudaSuccess)
         return cleanup(fail(F2D_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
     s->host_pipeline = env_int("F2D_HOST_PIPELINE", 1) != 0;
+    s->host_pipeline_min_bytes = (size_t)env_int("F2D_HOST_PIPELINE_MIN_BYTES", 1 << 20);
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
         return cleanup(fail(F2D_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError())));
     if (cudaStreamSynchronize(s->stream) != cudaSuccess)
@@ -1518,7 +1520,7 @@ F2D_API int f2d_solve_host(f2d_solver* s, float* density, const float* density_s
     const size_t host_bytes = (size_t)s->g.rows * s->g.cols * sizeof(float);
     const void* hosts[6] = {density, u, v, density_source, u_source, v_source};
     for (const void* h : hosts) s->pin_host(h, host_bytes);
-    if (s->host_pipeline && !s->multi() && !s->cpu_sem()) {
+    if (s->host_pipeline && !s->multi() && !s->cpu_sem() && s->field_bytes >= s->host_pipeline_min_bytes) {
         F2D_TRY(s->solve_host_pipelined(density, density_source, diffusion_rate, u, v, u_source, v_source, viscosity, dt));
         return f2d_sync(s);
     }

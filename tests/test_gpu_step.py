@@ -82,6 +82,7 @@ def test_pipelined_solve_host_equals_plain_and_keeps_state(f2d, sfo, gpu_ok, mon
     results = {}
     for pipe in ("1", "0"):
         monkeypatch.setenv("F2D_HOST_PIPELINE", pipe)
+        monkeypatch.setenv("F2D_HOST_PIPELINE_MIN_BYTES", "0")  # by default fields under 1 MiB take the serial order
         hd, hu, hv = f[0].copy(), f[1].copy(), f[2].copy()
         with f2d.FluidSolverB200(n, n, diffuse_iters=kd, project_iters=kp, divide_mode=DIV_F64, use_graph=graph) as s:
             for _ in range(2):
