@@ -39,12 +39,17 @@ namespace f2d {
 
 namespace {
 constexpr int kGsWarps = 4;
-constexpr unsigned kSpinLimit = 1u << 24;  // polls before a wait gives up and raises the error flag (seconds)
+constexpr unsigned long long kWaitLimitNs = 30ull * 1000ull * 1000ull * 1000ull;  // a wait longer than this raises the error flag
 
 __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -59,6 +64,7 @@ __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned
     // polls are relaxed loads (served by L2, no L1 invalidation per poll); one acquire fence once the value is in
     unsigned v = __shfl_sync(0xffffffffu, ld_relaxed(flag), 0);
     unsigned spins = 0, ns = 0;
+    unsigned long long t_start = 0;
     while (v < need) {
         // a neighbour one tile behind arrives within a few polls: spin, then back off gently.  One that is several
         // tiles behind (a band that has not reached this column yet, a later sweep waiting for its turn) cannot
@@ -73,7 +79,9 @@ __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned
         v = __shfl_sync(0xffffffffu, ld_relaxed(flag), 0);
         if ((++spins & 255u) == 0u) {
             if (__shfl_sync(0xffffffffu, *reinterpret_cast<volatile int*>(err), 0)) break;
-            if (spins >= kSpinLimit) {
+            const unsigned long long now = __shfl_sync(0xffffffffu, global_ns(), 0);
+            if (t_start == 0) t_start = now;
+            if (now - t_start > kWaitLimitNs) {
                 if (lane == 0) atomicExch(err, 1);
                 break;
             }

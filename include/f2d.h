@@ -113,7 +113,10 @@ F2D_API void f2d_destroy(f2d_solver* s);
 /* ---- the reference interface ------------------------------------------------------------
  * fluid_solver::solve (src/fluid_solver.hpp:16-24; GPU: src/fluid_solver_gpu.cu:222-258):
  * host arrays (row-major, pitch == cols, like grid<float>::data()), density/u/v updated in
- * place, sources const.  Upload -> one device step -> download; blocking. */
+ * place, sources const.  Upload -> one device step -> download; blocking.  On one GPU with fields of >= 1 MiB the
+ * three phases overlap: uploads in the order u, su, v, sv, sd, d; the step cut into four parts that start as their
+ * inputs land; the velocity downloaded while the density is still being solved.  The
+ * device-resident state afterwards equals the host grids. */
 F2D_API int f2d_solve_host(f2d_solver* s, float* density, const float* density_source, float diffusion_rate,
                    float* u, float* v, const float* u_source, const float* v_source, float viscosity,
                    float dt);
