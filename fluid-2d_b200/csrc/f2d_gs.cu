@@ -35,6 +35,10 @@ extern "C" __attribute__((visibility("default"))) int f2d_debug_gs_cycles(unsign
 #define GS_ACC(i, a, b)
 #endif
 
+#ifndef F2D_GS_MINB
+#define F2D_GS_MINB 4  // resident CTAs per SM the register allocator must allow (A/B: tools/build_variants.sh gs)
+#endif
+
 namespace f2d {
 
 namespace {
@@ -97,7 +101,7 @@ __device__ __forceinline__ unsigned wait_at_least(const unsigned* flag, unsigned
 // LOWER ticket, i.e. to a warp that is already running or finished: the wavefront cannot deadlock however many
 // warps the grid has and however few are resident.
 template <bool DIFFUSE>
-__global__ void __launch_bounds__(kGsWarps * 32, 4) k_gs_relax(GsBatch b) {
+__global__ void __launch_bounds__(kGsWarps * 32, F2D_GS_MINB) k_gs_relax(GsBatch b) {
     __shared__ float smem[kGsWarps][gs::kWarpFloats];
     const int lane = threadIdx.x & 31;
     float* tile = smem[threadIdx.x >> 5] + gs::kPad;

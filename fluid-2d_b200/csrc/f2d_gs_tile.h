@@ -42,7 +42,10 @@ constexpr int kRhsFloats = kBand * kTileCols;      // right-hand side tile (pitc
 // One warp's on-chip block: [kPad slack][value tile][rhs tile][kPad slack], contiguous.  The step loop addresses its
 // operands with unclamped column offsets; a lane whose column is outside the tile (the skew's ramp-up / ramp-down)
 // then reads up to 31 floats before or after its row.  Those reads are discarded, the slack keeps them in bounds.
-constexpr int kPad = 64;
+#ifndef F2D_GS_PAD
+#define F2D_GS_PAD 64
+#endif
+constexpr int kPad = F2D_GS_PAD;  // >= 32
 constexpr int kWarpFloats = kPad + kTileFloats + kRhsFloats + kPad;
 
 // boundary kinds as in include/f2d.h
