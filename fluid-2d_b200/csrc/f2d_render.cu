@@ -3,8 +3,9 @@
 // The reference re-uploads the host grids every frame, runs one kernel, downloads the result and
 // hands it to SFML (src/density_grid_renderer.cu:38-56, src/velocity_grid_renderer.cu:55-72).  Here
 // the solver's own device fields are the input; the output goes to a host buffer (image / line list)
-// and no window system is involved.  Not on the hot path; arithmetic restated from the reference
-// kernels (SFML is absent, so the reference renderers cannot be compiled here: parity unpinned).
+// and no window system is involved.  Not on the hot path; the arithmetic follows the SASS of the reference
+// kernels (FMUL / FMNMX / F2I.U32 for the image; FMUL, IEEE divide, FADD -- no FMA -- for the segments) and the
+// output is bit-identical to theirs (tests/test_gpu_render_ref.py).
 #include "f2d_kernels.cuh"
 
 namespace f2d {

@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CPU_PATH = os.path.join(_HERE, "_ref", "libref_cpu.so")
 GPU_PATH = os.path.join(_HERE, "_ref", "libref_gpu.so")
+RENDER_PATH = os.path.join(_HERE, "_ref", "libref_render.so")
 _FP = C.POINTER(C.c_float)
 _cpu = None
 _gpu = None
@@ -158,3 +159,55 @@ def ref_cpu():
 
 def ref_gpu():
     return _Ref("gpu")
+
+
+# ---- the reference's renderers (src/density_grid_renderer.cu, src/velocity_grid_renderer.cu), unmodified, compiled
+# against oracle/sfml_stub: what the app would hand to SFML for a given field
+_render = None
+
+
+def have_render():
+    """True when libref_render.so exists AND a CUDA device is visible."""
+    if not os.path.exists(RENDER_PATH):
+        return False
+    try:
+        return render_lib().ref_render_device_count() > 0
+    except OSError:
+        return False
+
+
+def render_lib():
+    global _render
+    if _render is None:
+        L = C.CDLL(RENDER_PATH)
+        L.ref_render_device_count.restype = C.c_int
+        L.ref_render_density.argtypes = [C.c_size_t, _FP, C.c_float, C.c_float, C.c_float, C.c_uint, C.c_uint,
+                                         C.POINTER(C.c_ubyte)]
+        L.ref_render_density.restype = C.c_int
+        L.ref_render_velocity.argtypes = [C.c_size_t, _FP, _FP, C.c_uint, C.c_uint, _FP, C.POINTER(C.c_int)]
+        L.ref_render_velocity.restype = C.c_int
+        _render = L
+    return _render
+
+
+def ref_render_density(d, mult, target=(800, 800)):
+    """density_grid_renderer::draw: (n, n, 4) uint8 RGBA."""
+    d = _c(d)
+    n = d.shape[0]
+    img = np.empty((n, n, 4), np.uint8)
+    rc = render_lib().ref_render_density(n, _p(d), mult[0], mult[1], mult[2], target[0], target[1],
+                                         img.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    assert rc == 0, rc
+    return img
+
+
+def ref_render_velocity(u, v, target=(800, 800)):
+    """velocity_grid_renderer::draw: (n, n, 4) float32 segments (start.x, start.y, end.x, end.y); the scales are
+    target / grid as the reference computes them (src/velocity_grid_renderer.cu:64)."""
+    u, v = _c(u), _c(v)
+    n = u.shape[0]
+    ln = np.empty((n, n, 4), np.float32)
+    ok = C.c_int(0)
+    rc = render_lib().ref_render_velocity(n, _p(u), _p(v), target[0], target[1], ln.ctypes.data_as(_FP), C.byref(ok))
+    assert rc == 0 and ok.value == 1, (rc, ok.value)
+    return ln

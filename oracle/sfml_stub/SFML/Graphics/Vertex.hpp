@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY: see ../Graphics.hpp
+#pragma once
+#include "../Graphics.hpp"

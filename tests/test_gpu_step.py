@@ -170,7 +170,7 @@ def test_live_against_unmodified_reference_gpu_solver(f2d, gpu_ok):
 def test_headless_renderers_match_restatement(f2d, gpu_ok):
     """density -> RGBA8 (src/density_grid_renderer.cu:10-29) and velocity -> line list
     (src/velocity_grid_renderer.cu:8-44) on the device-resident fields, against a numpy restatement
-    (the reference renderers need SFML and cannot be compiled here: parity unpinned)."""
+    (a second, independent check; the reference's own renderers are the pin: tests/test_gpu_render_ref.py)."""
     n = 72
     d, u, v, *_ = rng_fields(n, 77)
     d = (d * np.float32(3.0) - np.float32(0.5)).astype(np.float32)  # exercise both clamps
