@@ -3,7 +3,8 @@
 // (src/simulation.hpp:64-77), source injection scaled by width*height (src/simulation.cpp:44-51),
 // update() = solve() then zero the sources (src/simulation.cpp:53-65), reset() zeroes the state
 // (src/simulation.cpp:29-34), solver chosen by an enum (src/simulation.hpp:14, src/simulation.cpp:17-26).
-// The draw()/coordinates_to_cell() halves of the reference class are renderer concerns and not here.
+// coordinates_to_cell() is grid_renderer's mouse -> cell mapping (src/grid_renderer.cpp:3-14, reached through
+// src/simulation.cpp:36-42); draw() is replaced by draw_density_ppm().
 #pragma once
 
 #include <algorithm>
@@ -21,6 +22,17 @@
 //   b200            the arithmetic of fluid_solver_gpu (the reference's default solver, src/app.cpp:32)
 //   b200_cpu_exact  the arithmetic of fluid_solver_cpu, bit for bit (F2D_SEM_CPU: Gauss-Seidel, 20 iterations, no smooth)
 enum class solver_type { b200, b200_cpu_exact };
+
+// grid_renderer::coordinates_to_cell (src/grid_renderer.cpp:3-14) without SFML: target position (x, y) on a target of
+// target_w x target_h pixels -> grid cell (i, j); false outside the target.  The grid is taken to be stretched over
+// the target: float quotient, float product with the size_t extent, truncation -- as the reference computes it.
+inline bool coordinates_to_cell(size_t const rows, size_t const cols, float const x, float const y, unsigned const target_w,
+                                unsigned const target_h, size_t& i, size_t& j) {
+    if (x < 0.f || y < 0.f || x >= target_w || y >= target_h) return false;
+    i = static_cast<size_t>(rows * (y / target_h));
+    j = static_cast<size_t>(cols * (x / target_w));
+    return true;
+}
 
 struct simulation_config {
     size_t width = 800;             // src/app.cpp:30-31
@@ -58,6 +70,12 @@ public:
         std::fill(m_density_grid.begin(), m_density_grid.end(), 0.f);
         std::fill(m_horizontal_velocity_grid.begin(), m_horizontal_velocity_grid.end(), 0.f);
         std::fill(m_vertical_velocity_grid.begin(), m_vertical_velocity_grid.end(), 0.f);
+    }
+
+    // the mouse -> cell mapping of src/simulation.cpp:36-42
+    bool coordinates_to_cell(float const x, float const y, unsigned const target_w, unsigned const target_h, size_t& i,
+                             size_t& j) const {
+        return ::coordinates_to_cell(m_config.height, m_config.width, x, y, target_w, target_h, i, j);
     }
 
     void add_density_source(size_t const i, size_t const j, float const value) {

@@ -115,3 +115,35 @@ def test_headless_run_cpu_exact_solver_is_bit_identical_to_fluid_solver_cpu(f2d,
             d, u, v = sfo.steps(d, sd, 0.5, u, v, su, sv, 1e-6, 0.02, 20, 20, smooth=False, sem=sfo.SEM_CPU, nsteps=1)
     for name, want in (("density", d), ("u", u), ("v", v)):
         assert_bitwise(np.load(prefix + "_%s.npy" % name), want, name)
+
+
+def test_coordinates_to_cell_matches_reference_grid_renderer(f2d, tmp_path):
+    """The mouse -> cell mapping (include/simulation_headless.hpp) against the UNMODIFIED grid_renderer::
+    coordinates_to_cell (src/grid_renderer.cpp:3-14, compiled against oracle/sfml_stub into oracle/_ref/libref_gridr.so)."""
+    import ctypes as C
+
+    ref_path = os.path.join(ROOT, "oracle", "_ref", "libref_gridr.so")
+    if not os.path.exists(ref_path):
+        pytest.skip("oracle/_ref/libref_gridr.so not built (needs /root/reference)")
+    src = tmp_path / "c2c.cpp"
+    src.write_text('''#include "simulation_headless.hpp"
+extern "C" int ours_coordinates_to_cell(size_t rows, size_t cols, float x, float y, unsigned tw, unsigned th, size_t* i, size_t* j) {
+    return coordinates_to_cell(rows, cols, x, y, tw, th, *i, *j) ? 1 : 0;
+}''')
+    lib = tmp_path / "libc2c.so"
+    libdir = os.path.join(ROOT, "fluid-2d_b200")
+    subprocess.run(["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include"), str(src), "-L", libdir,
+                    "-lf2d", "-Wl,-rpath," + libdir, "-o", str(lib)], check=True)
+    ours, ref = C.CDLL(str(lib)).ours_coordinates_to_cell, C.CDLL(ref_path).ref_coordinates_to_cell
+    for fn in (ours, ref):
+        fn.argtypes = [C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_uint, C.c_uint, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        fn.restype = C.c_int
+    r = np.random.default_rng(5)
+    for rows, cols, tw, th in ((800, 800, 800, 800), (256, 256, 800, 800), (100, 37, 641, 479), (4096, 4096, 1000, 3)):
+        xs = np.concatenate([r.uniform(-5, tw + 5, 400), [0.0, tw - 1e-3, tw, -0.0, 0.5]]).astype(np.float32)
+        ys = np.concatenate([r.uniform(-5, th + 5, 400), [0.0, th - 1e-3, th, 1.0, th / 2]]).astype(np.float32)
+        for x, y in zip(xs, ys):
+            a, b = (C.c_size_t(12345), C.c_size_t(54321)), (C.c_size_t(12345), C.c_size_t(54321))
+            ra = ours(rows, cols, float(x), float(y), tw, th, C.byref(a[0]), C.byref(a[1]))
+            rb = ref(rows, cols, float(x), float(y), tw, th, C.byref(b[0]), C.byref(b[1]))
+            assert (ra, a[0].value, a[1].value) == (rb, b[0].value, b[1].value), (rows, cols, tw, th, x, y)
