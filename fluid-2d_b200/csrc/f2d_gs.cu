@@ -15,6 +15,7 @@
 // (cpp:190-193, :207-211 vs gpu.cu:173-174, :202-203) and reuse the kernels of f2d_kernels_simple.cu.
 #include "f2d_gs_tile.h"
 #include "f2d_kernels.cuh"
+#include "f2d_scatter_core.h"
 
 #ifdef F2D_GS_TIMING
 // Profiling build only (tools/gs_timing.py): cycles per phase of a tile, summed over all warps.
@@ -265,40 +266,26 @@ void launch_advect_velocity_nofma(const Geom& g, const float* u0, const float* v
 }
 
 // ----------------------------------------------------------------------- advect (ordered scatter)
-// cpp:127-152 turned inside out.  The reference zeroes the field, then walks the sources (i,j) in lexicographic
-// order and adds four weighted copies of each into the cells around its forward-traced position.  A target cell
-// therefore receives its contributions in lexicographic SOURCE order, and float addition makes that order part of
-// the result.  Two passes, no atomics on the data:
-//   k_scatter_keys     one thread per source: the landing cell (i0, j0) as a linear index, or ~0 if the source is
-//                      skipped (cpp:134); also the largest displacement max(|dt0*u|, |dt0*v|) as the bit pattern of
-//                      a non-negative float (integer max == float max there; a NaN compares above everything and
-//                      widens the scan to the whole grid);
-//   k_scatter_ordered  one thread per interior target: visits, in lexicographic order, every source whose
-//                      displacement can reach it (|di|, |dj| <= R = ceil(max displacement) + 1); a source lands
-//                      here iff target - key is one of {0, 1, pitch, pitch + 1}; only then its position is
-//                      recomputed exactly as the reference does (product rounded, then added) and its share added.
-// Edge cells and corners are overwritten by the boundary pass that follows (cpp:176), so only the interior is
-// produced.
-constexpr unsigned kNoKey = 0xffffffffu;
-
-__device__ __forceinline__ bool forward_trace(const Geom& g, int i, int j, float uu, float vv, float dt0, float& x, float& y) {
-    x = __fadd_rn((float)j, __fmul_rn(dt0, uu));
-    y = __fadd_rn((float)i, __fmul_rn(dt0, vv));
-    return !(x < 0.5f || x > (float)g.cols - 1.5f || y < 0.5f || y > (float)g.rows - 1.5f);
-}
-
+// cpp:127-152 turned inside out (algorithm and per-cell functions: f2d_scatter_core.h).  Two passes, no atomics on
+// the data:
+//   k_scatter_keys     one thread per source: its landing cell as a linear index (or kNoKey), and the largest
+//                      displacement max(|dt0*u|, |dt0*v|) as the bit pattern of a non-negative float (integer max ==
+//                      float max there; a NaN compares above everything and widens the scan to the whole grid);
+//   k_scatter_ordered  one thread per interior target: visits, in lexicographic order, every source whose displacement
+//                      can reach it (|di|, |dj| <= R = ceil(max displacement) + 1) and adds the share of those that
+//                      land on it.  Edge cells and corners are overwritten by the boundary pass that follows
+//                      (cpp:176), so only the interior is produced.
 __global__ void __launch_bounds__(256) k_scatter_keys(Geom g, const float* __restrict__ u, const float* __restrict__ v, float dt0,
                                                      unsigned* __restrict__ keys, unsigned* disp_bits) {
     const int j = blockIdx.x * 32 + threadIdx.x, i = blockIdx.y * 8 + threadIdx.y;
     unsigned m = 0u;
     if (i < g.rows && j < g.cols) {
         const size_t o = (size_t)i * g.pitch + j;
-        unsigned key = kNoKey;
+        unsigned key = sc::kNoKey;
         if (i >= 1 && i <= g.rows - 2 && j >= 1 && j <= g.cols - 2) {
             const float uu = __ldg(u + o), vv = __ldg(v + o);
             m = max(__float_as_uint(fabsf(__fmul_rn(dt0, uu))), __float_as_uint(fabsf(__fmul_rn(dt0, vv))));
-            float x, y;
-            if (forward_trace(g, i, j, uu, vv, dt0, x, y)) key = (unsigned)(int)y * (unsigned)g.pitch + (unsigned)(int)x;
+            key = sc::source_key(g.rows, g.cols, g.pitch, i, j, uu, vv, dt0);
         }
         keys[o] = key;
     }
@@ -312,9 +299,7 @@ __global__ void __launch_bounds__(256) k_scatter_ordered(Geom g, const float* __
                                                         float* __restrict__ out, float dt0, const unsigned* __restrict__ disp_bits) {
     const int tj = 1 + blockIdx.x * 32 + threadIdx.x, ti = 1 + blockIdx.y * 8 + threadIdx.y;
     if (ti > g.rows - 2 || tj > g.cols - 2) return;
-    const float md = __uint_as_float(*disp_bits);
-    const int far = max(g.rows, g.cols);
-    const int R = (md < (float)far) ? (int)ceilf(md) + 1 : far;  // also catches NaN / inf
+    const int R = sc::reach(*disp_bits, max(g.rows, g.cols));
     const int ilo = max(1, ti - R), ihi = min(g.rows - 2, ti + R);
     const int jlo = max(1, tj - R), jhi = min(g.cols - 2, tj + R);
     const unsigned P = (unsigned)g.pitch, T = (unsigned)ti * P + (unsigned)tj;
@@ -322,14 +307,9 @@ __global__ void __launch_bounds__(256) k_scatter_ordered(Geom g, const float* __
     for (int i = ilo; i <= ihi; ++i) {
         const size_t row = (size_t)i * g.pitch;
         for (int j = jlo; j <= jhi; ++j) {
-            const unsigned d = T - __ldg(keys + row + j);  // kNoKey gives T + 1 >= pitch + 2: never a hit
-            if (d > P + 1u || (d > 1u && d < P)) continue;
-            float x, y;
-            forward_trace(g, i, j, __ldg(u + row + j), __ldg(v + row + j), dt0, x, y);
-            const Bilinear b = bilinear_setup(x, y);
-            const float wx = (d == 1u || d == P + 1u) ? b.s0 : b.s1;  // landed one column left of the target: right-hand weight
-            const float wy = (d >= P) ? b.s2 : b.s3;                  // landed one row above the target: lower weight
-            acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(wx, wy), __ldg(src + row + j)));
+            const unsigned d = T - __ldg(keys + row + j);
+            if (!sc::is_hit(d, P)) continue;
+            acc = __fadd_rn(acc, sc::share(g.rows, g.cols, i, j, __ldg(u + row + j), __ldg(v + row + j), dt0, d, P, __ldg(src + row + j)));
         }
     }
     out[(size_t)ti * g.pitch + tj] = acc;
