@@ -11,24 +11,26 @@ from bench import DIFFUSION_RATE, DT, METRIC, UNIT, VISCOSITY, ClockSampler, mea
 
 def canonical_rows(n, r0, r1):
     """Rows [r0, r1) of the canonical fields, generated locally (no full-grid host arrays)."""
-    import ctypes as C
+    from tools import canonical as _c
 
-    from oracle import sfo
+    return list(_c.rows(n, r0, r1))
 
-    L = sfo.lib()
-    rows = r1 - r0
-    arrs = [np.empty((rows, n), dtype=np.float32) for _ in range(6)]
-    fp = C.POINTER(C.c_float)
-    # sfo_canonical_fields indexes the FULL field: pass pointers shifted back by r0 rows
-    ptrs = [C.cast(a.ctypes.data - r0 * n * 4, fp) for a in arrs]
-    import threading
 
-    nthr = min(16, os.cpu_count() or 1, max(1, rows // 256))
-    bounds = np.linspace(r0, r1, nthr + 1).astype(int)
-    ts = [threading.Thread(target=L.sfo_canonical_fields, args=(n, int(bounds[k]), int(bounds[k + 1]), *ptrs)) for k in range(nthr)]
-    [t.start() for t in ts]
-    [t.join() for t in ts]
-    return arrs
+def single_gpu_base(f2d, n, kd, kp, device=0, steps=5):
+    """The N > 1 workload (n x n, Kd, Kp) on ONE GPU, device-resident: the denominator of strong-scaling efficiency.
+    Measured inside the run that reports the efficiency (rank 0, after the slab solvers are gone)."""
+    fb = canonical_rows(n, 0, n)
+    with f2d.FluidSolverB200(n, n, diffuse_iters=kd, project_iters=kp, device=device) as sb:
+        sb.upload(*fb[:3])
+        sb.set_sources(*fb[3:])
+        del fb
+        sb.step(DIFFUSION_RATE, VISCOSITY, DT, 3)
+        sb.sync()
+        b_ms = sb.step_timed(DIFFUSION_RATE, VISCOSITY, DT, steps) / steps
+        sb.sync()
+    return {"workload": "%dx%d grid, Kd=Kp=%d on ONE GPU (the workload of the N > 1 runs), device-resident" % (n, n, kd),
+            "value": float(n) * n / (b_ms * 1e-3), "unit": UNIT, "ms_per_step": b_ms, "steps": steps,
+            "note": "strong-scaling efficiency of an N-GPU line = its value / (N * this value)"}
 
 
 def run_multi_gpu(args, workload):
@@ -71,10 +73,11 @@ def run_multi_gpu(args, workload):
         sampler.start()
         time.sleep(0.3)
     barrier()
-    l0, x0 = solver.launch_count(), slabmod.comm_exchanges(solver)
+    l0, x0, b0 = solver.launch_count(), slabmod.comm_exchanges(solver), slabmod.comm_bytes(solver)
     ms = solver.step_timed(DIFFUSION_RATE, VISCOSITY, DT, args.steps)
     barrier()
     launches, xch = solver.launch_count() - l0, slabmod.comm_exchanges(solver) - x0
+    halo_stats = {"bytes_per_neighbour_per_step": (slabmod.comm_bytes(solver) - b0) / max(1, args.steps)}
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
@@ -116,11 +119,24 @@ def run_multi_gpu(args, workload):
         value = cells * args.steps / (ms_max * 1e-3)
         peak, peak_src = measured_peaks()
         bps = step_bytes(kd, kp)
-        halo_bytes = xch / max(1, args.steps) * halo * n * 4  # per neighbour per direction per step (<= 3 fields/exchange)
-        from bench import cpu_reference_solver, canonical
+        from bench import run_leg
 
-        run, kind = cpu_reference_solver()
-        cpu_t = run(canonical(2048), kd, kp)
+        # strong-scaling base, same run, same box: the SAME grid and K on one GPU (the other ranks wait in the barrier)
+        base = None
+        if os.environ.get("F2D_BENCH_SCALING_BASE", "1") == "1":
+            try:
+                base = single_gpu_base(f2d, n, kd, kp, device=local_rank)
+            except Exception as e:
+                base = {"unavailable": str(e)[:200]}
+        speedup = efficiency = None
+        if base and "value" in base:
+            speedup = value / base["value"]
+            efficiency = speedup / world
+        # NVLink traffic of the halo exchanges: bytes this rank pushes to ONE neighbour per step, and the rate if the
+        # whole step's push were spread over the step time (the exchanges are latency-, not bandwidth-bound)
+        push_bytes = halo_stats["bytes_per_neighbour_per_step"]
+        nvlink_peak = 900.0  # GB/s per direction per GPU, nominal (B200_PROFILING.md; measured peer copy 770)
+        cpu = run_leg("cpu_baseline", 2048, kd, 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": workload["scaling"],
@@ -130,19 +146,27 @@ def run_multi_gpu(args, workload):
                        "transport": getattr(solver, "transport", transport),
                        "temporal_block": int(cfg.temporal_block), "temporal_block_diffuse": int(cfg.temporal_block_diffuse), "jacobi_mode": int(cfg.jacobi_mode),
                        "divide_mode": int(cfg.divide_mode), "cfl_cells": cfl,
+                       "scaling_base_ms_per_step": None if not base else base.get("ms_per_step"),
+                       "scaling_base_value": None if not base else base.get("value"),
+                       "speedup_vs_1gpu_same_grid": speedup, "efficiency": efficiency,
                        "l2": "inputs larger than L2 (slab fields of %.0f MiB)" % (sl.rows * n * 4 / 2**20)},
             "roofline": {"bound": "hbm", "kernel": "whole step, algorithmic bytes (SURVEY 8d)", "achieved": bps * value / 1e9,
                          "peak": peak * world, "unit": "GB/s", "frac": bps * value / 1e9 / (peak * world), "traffic": None,
                          "peak_source": peak_src + " x n_gpus",
-                         "halo": {"exchanges_per_step": xch / max(1, args.steps), "rows": halo,
-                                  "approx_bytes_per_neighbour_per_step": halo_bytes}},
-            "cpu_baseline": {"value": 2048 * 2048 / cpu_t, "unit": UNIT, "cores": 1, "kind": kind,
-                             "sample": "1 step of a 2048x2048 grid, Kd=Kp=%d, fluid_solver_cpu (1 thread)" % kd},
+                         "halo_exchanges_per_step": xch / max(1, args.steps), "halo_rows": halo,
+                         "halo_bytes_per_neighbour_per_step": push_bytes,
+                         "nvlink_gbs_avg_over_step": push_bytes / (ms_max / args.steps * 1e-3) / 1e9,
+                         "nvlink_frac_of_900": push_bytes / (ms_max / args.steps * 1e-3) / 1e9 / nvlink_peak,
+                         "nvlink_time_at_900_ms": push_bytes / (nvlink_peak * 1e9) * 1e3},
+            "cpu_baseline": cpu if "unavailable" in cpu else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(6 * 4 * cells),
-                    "d2h_bytes_per_step": int(3 * 4 * cells), "steps": e2e_steps,
+                    "d2h_bytes_per_step": int(3 * 4 * cells), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
                     "api": "FluidSolverB200.solve per slab (pinned host slabs, halo rows included)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
+            "scaling_base": base,
+            "speedup": speedup,
+            "efficiency": efficiency,
         }
         print(json.dumps(line), flush=True)
     dist.barrier()

@@ -59,7 +59,7 @@ def build(force=False):
     srcdir = os.path.join(_HERE, "csrc")
     if not force and os.path.exists(_LIB):
         newest = max(os.path.getmtime(os.path.join(srcdir, f)) for f in os.listdir(srcdir)
-                     if f.endswith((".cu", ".cuh")))
+                     if f.endswith((".cu", ".cuh", ".h")) or f == "Makefile")
         newest = max(newest, os.path.getmtime(_HEADER))
         if os.path.getmtime(_LIB) >= newest:
             return _LIB
@@ -117,6 +117,9 @@ def load():
         "f2d_comm_unique_id": [C.c_char_p],
         "f2d_comm_init": [vp, C.c_char_p, i32, i32, i32],
         "f2d_comm_stats": [vp, C.POINTER(C.c_uint64)],
+        "f2d_comm_bytes": [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
+        "f2d_pin_host": [vp, vp, C.c_size_t],
+        "f2d_unpin_host": [vp, vp],
         "f2d_p2p_export": [vp, C.POINTER(C.c_ubyte), C.POINTER(C.c_uint64)],
         "f2d_p2p_connect": [vp, i32, i32, C.POINTER(C.c_ubyte), C.POINTER(C.c_uint64), C.POINTER(C.c_ubyte),
                             C.POINTER(C.c_uint64), i32],

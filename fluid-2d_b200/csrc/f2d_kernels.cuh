@@ -91,6 +91,7 @@ struct XchgParams {
     unsigned* my_flags;    // this rank's flag block
     unsigned* up_flags;    // the neighbours' flag blocks (peer-mapped), nullptr at the global edges
     unsigned* down_flags;
+    unsigned long long timeout_ns;  // wall-clock bound of every wait
 };
 void launch_halo_xchg(const XchgParams& p, cudaStream_t st);
 

@@ -12,8 +12,8 @@
 //      (my own halos are then complete) and advances the epoch.
 //
 // All flags are monotonically increasing epochs in device memory, so the same kernels replay inside a
-// CUDA graph step after step.  Every wait is bounded: on a timeout the error flag is raised (reported by
-// f2d_sync) and the kernel exits instead of hanging the GPU.
+// CUDA graph step after step.  Every wait is bounded in wall-clock time (default 30 s, F2D_P2P_TIMEOUT_MS): on a
+// timeout the error flag is raised (reported and cleared by f2d_sync) and the kernel exits instead of hanging the GPU.
 #include "f2d_kernels.cuh"
 
 namespace f2d {
@@ -30,12 +30,22 @@ __device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
 __device__ __forceinline__ void st_flag(unsigned* p, unsigned v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void wait_flag(const unsigned* p, unsigned e, unsigned* err) {
+__device__ __forceinline__ unsigned long long wall_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded by WALL-CLOCK time (%globaltimer), not by a poll count: a neighbour may legitimately lag by seconds
+// (first-step graph instantiation, module load, host jitter).  After `timeout_ns` without progress -- or as soon as
+// an earlier wait of this rank has timed out -- the error flag is raised (f2d_sync reports and clears it) and the
+// kernel moves on instead of hanging the device.
+__device__ __forceinline__ void wait_flag(const unsigned* p, unsigned e, unsigned* err, unsigned long long timeout_ns) {
+    if ((int)(ld_flag(p) - e) >= 0) return;
+    const unsigned long long t0 = wall_ns();
     unsigned it = 0;
     while ((int)(ld_flag(p) - e) < 0) {
-        __nanosleep(128);
-        // ~2 s without progress (or an earlier timeout): the neighbour is gone; never hang the device
-        if (++it > (1u << 22) || (it % 1024u == 0 && ld_flag(err) != 0u)) {
+        __nanosleep(64);
+        if ((++it & 255u) == 0u && (wall_ns() - t0 > timeout_ns || ld_flag(err) != 0u)) {
             atomicExch(err, 1u);
             break;
         }
@@ -53,8 +63,8 @@ __global__ void __launch_bounds__(256) k_halo_xchg(XchgParams P) {
             if (P.up_flags) st_flag(P.up_flags + FL_READY_FROM_DOWN, e);
             if (P.down_flags) st_flag(P.down_flags + FL_READY_FROM_UP, e);
         }
-        if (P.up_flags) wait_flag(mf + FL_READY_FROM_UP, e, mf + FL_ERROR);
-        if (P.down_flags) wait_flag(mf + FL_READY_FROM_DOWN, e, mf + FL_ERROR);
+        if (P.up_flags) wait_flag(mf + FL_READY_FROM_UP, e, mf + FL_ERROR, P.timeout_ns);
+        if (P.down_flags) wait_flag(mf + FL_READY_FROM_DOWN, e, mf + FL_ERROR, P.timeout_ns);
     }
     __syncthreads();
     const unsigned e = e_s;
@@ -73,8 +83,8 @@ __global__ void __launch_bounds__(256) k_halo_xchg(XchgParams P) {
             __threadfence_system();
             if (P.up_flags) st_flag(P.up_flags + FL_DONE_FROM_DOWN, e);
             if (P.down_flags) st_flag(P.down_flags + FL_DONE_FROM_UP, e);
-            if (P.up_flags) wait_flag(mf + FL_DONE_FROM_UP, e, mf + FL_ERROR);
-            if (P.down_flags) wait_flag(mf + FL_DONE_FROM_DOWN, e, mf + FL_ERROR);
+            if (P.up_flags) wait_flag(mf + FL_DONE_FROM_UP, e, mf + FL_ERROR, P.timeout_ns);
+            if (P.down_flags) wait_flag(mf + FL_DONE_FROM_DOWN, e, mf + FL_ERROR, P.timeout_ns);
             __threadfence_system();
             st_flag(mf + FL_EPOCH, e);
         }

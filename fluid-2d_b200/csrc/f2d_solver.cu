@@ -92,12 +92,12 @@ struct f2d_solver {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_density = nullptr, ev_copy = nullptr;
     bool capturing = false;
-    bool host_register = true;
+    bool host_register = false;  // F2D_HOST_REGISTER=1: f2d_solve_host registers every grid it sees (opt-in, see f2d.h)
     void* render_buf = nullptr;  // scratch of the headless renderers
     size_t render_bytes = 0;
     bool fuse_sources = true;     // F2D_FUSE_SOURCES=0: separate add_sources kernel (A/B, cross-check)
     bool fuse_divergence = true;  // F2D_FUSE_DIVERGENCE=0: separate divergence kernel (A/B, cross-check)
-    std::vector<void*> registered;  // host ranges this solver page-locked (cudaHostRegister)
+    std::vector<std::pair<void*, size_t>> registered;  // host ranges this solver page-locked (f2d_pin_host)
     // solve() pipeline (single GPU): the step cut into four parts, each launched as soon as ITS inputs are uploaded
     //   part 0: add_sources + diffuse u   (needs u, su)      part 2: project, advect, project   (needs parts 0, 1)
     //   part 1: add_sources + diffuse v   (needs v, sv)      part 3: the density chain          (needs d, sd, u, v)
@@ -174,12 +174,14 @@ struct f2d_solver {
         float* rx_down() const { return reinterpret_cast<float*>(arena + (size_t)nbuf * field_stride + rx_bytes); }
     };
     PeerLink peer_up, peer_down;
+    unsigned long long p2p_timeout_ns = 30ull * 1000000000ull;  // F2D_P2P_TIMEOUT_MS
     bool p2p = false;                            // halo transport: direct peer stores (true) or NCCL (comm != nullptr)
     int nbuffers() const { return 6 + (int)temps.size(); }
     int buffer_index(const float* p) const { return (int)((reinterpret_cast<const char*>(p) - arena) / (ptrdiff_t)field_stride); }
     int exchange_p2p(const float* const* bufs, int n);
     int reverse_exchange_p2p(float* buf);
     uint64_t exchanges = 0, exchanges_in_graph = 0;
+    uint64_t xbytes = 0, xbytes_in_graph = 0;  // payload bytes pushed to ONE neighbour (same for up and down)
     std::vector<std::pair<const float*, int>> inv_table;
 
     bool multi() const { return comm != nullptr || p2p; }
@@ -834,7 +836,7 @@ struct f2d_solver {
         if (last_div) release(last_div);
         if (last_p) release(last_p);
         last_div = last_p = nullptr;
-        const uint64_t before = launches, xbefore = exchanges;
+        const uint64_t before = launches, xbefore = exchanges, bbefore = xbytes;
         cudaGraph_t graph = nullptr;
         // relaxed mode: NCCL (multi-GPU) may issue its own runtime calls while we capture
         F2D_CUDA(cudaStreamBeginCapture(stream, multi() ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
@@ -851,6 +853,8 @@ struct f2d_solver {
         launches = before;  // capture launched nothing yet
         exchanges_in_graph = exchanges - xbefore;
         exchanges = xbefore;
+        xbytes_in_graph = xbytes - bbefore;
+        xbytes = bbefore;
         F2D_CUDA(cudaGraphInstantiate(&graph_exec, graph, 0));
         cudaGraphDestroy(graph);
         graph_key = {diffusion_rate, viscosity, dt, true};
@@ -865,6 +869,7 @@ struct f2d_solver {
                 F2D_CUDA(cudaGraphLaunch(graph_exec, stream));
                 launches += graph_kernels;
                 exchanges += exchanges_in_graph;
+                xbytes += xbytes_in_graph;
             }
         } else {
             for (uint32_t s = 0; s < nsteps; ++s)
@@ -873,8 +878,8 @@ struct f2d_solver {
         return F2D_OK;
     }
 
-    // Page-lock a caller's host grid once (grid<float> storage is pageable; the reference's copy()
-    // helpers pay the staged-copy price on every call, src/utilities.hpp:57-67).  Best effort.
+    // F2D_HOST_REGISTER=1 only (the caller then promises that every grid outlives the solver, f2d.h): page-lock a
+    // host grid on first sight.  The explicit, scoped way is f2d_pin_host / f2d_unpin_host.  Best effort.
     void pin_host(const void* p, size_t bytes) {
         if (!host_register || !p || bytes < (1u << 20)) return;  // small grids: the staged copy is cheap
         cudaPointerAttributes at;
@@ -884,7 +889,7 @@ struct f2d_solver {
         }
         if (at.type != cudaMemoryTypeUnregistered) return;
         if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess)
-            registered.push_back(const_cast<void*>(p));
+            registered.emplace_back(const_cast<void*>(p), bytes);
         else
             cudaGetLastError();
     }
@@ -990,6 +995,7 @@ int f2d_solver::exchange(const float* const* bufs, int n) {
     F2D_NCCL(g_nccl.GroupEnd());
     for (int i = 0; i < n; ++i) set_inv(bufs[i], 0);
     ++exchanges;
+    xbytes += (uint64_t)n * cnt * sizeof(float);
     return F2D_OK;
 }
 
@@ -1019,6 +1025,7 @@ int f2d_solver::reverse_exchange_add(float* buf) {
     }
     F2D_CUDA(cudaGetLastError());
     ++exchanges;
+    xbytes += (uint64_t)cnt * sizeof(float);
     set_inv(buf, H());
     return F2D_OK;
 }
@@ -1031,6 +1038,7 @@ int f2d_solver::exchange_p2p(const float* const* bufs, int n) {
     P.my_flags = flags;
     P.up_flags = has_up() ? peer_up.flags() : nullptr;
     P.down_flags = has_down() ? peer_down.flags() : nullptr;
+    P.timeout_ns = p2p_timeout_ns;
     P.nseg = 0;
     for (int i = 0; i < n; ++i) {
         const float* b = bufs[i];
@@ -1056,6 +1064,7 @@ int f2d_solver::exchange_p2p(const float* const* bufs, int n) {
     }
     F2D_CUDA(cudaGetLastError());
     for (int i = 0; i < n; ++i) set_inv(bufs[i], 0);
+    xbytes += (uint64_t)n * halo_floats * sizeof(float);
     return F2D_OK;
 }
 
@@ -1065,6 +1074,7 @@ int f2d_solver::reverse_exchange_p2p(float* buf) {
     P.my_flags = flags;
     P.up_flags = has_up() ? peer_up.flags() : nullptr;
     P.down_flags = has_down() ? peer_down.flags() : nullptr;
+    P.timeout_ns = p2p_timeout_ns;
     P.nseg = 0;
     // the partial sums in my halo rows go to the owner's landing zone: my top halo is the upper neighbour's
     // "from below" zone (rx_down there), my bottom halo the lower neighbour's "from above" zone (rx_up)
@@ -1084,6 +1094,7 @@ int f2d_solver::reverse_exchange_p2p(float* buf) {
     }
     F2D_CUDA(cudaGetLastError());
     ++exchanges;
+    xbytes += (uint64_t)n4 * 16u;
     set_inv(buf, H());
     return F2D_OK;
 }
@@ -1344,7 +1355,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     if (cudaMalloc(&s->oob_flag, sizeof(int)) != cudaSuccess)
         return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
     cudaMemsetAsync(s->oob_flag, 0, sizeof(int), s->stream);
-    s->host_register = env_int("F2D_HOST_REGISTER", 1) != 0;
+    s->host_register = env_int("F2D_HOST_REGISTER", 0) != 0;
     if (s->cpu_sem()) {
         const uint32_t k = std::max(3u * s->cfg.diffuse_iters, s->cfg.project_iters);
         s->gs_flag_cap = gs_flag_words(s->g.rows, 1, (int)std::max(k, 1u));
@@ -1364,6 +1375,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
         cudaEventCreateWithFlags(&s->ev_vel, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_fence, cudaEventDisableTiming) != cudaSuccess)
         return cleanup(fail(F2D_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError())));
+    s->p2p_timeout_ns = (unsigned long long)std::max(1, env_int("F2D_P2P_TIMEOUT_MS", 30000)) * 1000000ull;
     s->host_pipeline = env_int("F2D_HOST_PIPELINE", 1) != 0;
     s->host_pipeline_min_bytes = (size_t)env_int("F2D_HOST_PIPELINE_MIN_BYTES", 1 << 20);
     if (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)
@@ -1407,8 +1419,8 @@ F2D_API void f2d_destroy(f2d_solver* s) {
     }
     if (s->ev_density) cudaEventDestroy(s->ev_density);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
-    for (void* p : s->registered)
-        if (cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+    for (auto& r : s->registered)
+        if (cudaHostUnregister(r.first) != cudaSuccess) cudaGetLastError();
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -1418,6 +1430,41 @@ F2D_API void f2d_destroy(f2d_solver* s) {
         if (!(s)) return fail(F2D_ERR_INVALID, "solver is NULL"); \
         F2D_CUDA(cudaSetDevice((s)->device));                    \
     } while (0)
+
+F2D_API int f2d_pin_host(f2d_solver* s, const void* host, size_t bytes) {
+    F2D_NEED(s);
+    if (!host || bytes == 0) return fail(F2D_ERR_INVALID, "NULL host pointer or empty range");
+    for (auto& r : s->registered)
+        if (r.first == host) return r.second >= bytes ? F2D_OK : fail(F2D_ERR_STATE, "range already pinned with a smaller size");
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) return F2D_OK;  // already page-locked
+    cudaGetLastError();
+    F2D_CUDA(cudaHostRegister(const_cast<void*>(host), bytes, cudaHostRegisterDefault));
+    s->registered.emplace_back(const_cast<void*>(host), bytes);
+    return F2D_OK;
+}
+
+F2D_API int f2d_unpin_host(f2d_solver* s, const void* host) {
+    F2D_NEED(s);
+    for (size_t i = 0; i < s->registered.size(); ++i)
+        if (s->registered[i].first == host) {
+            // no copy of this solver may still be using the range
+            F2D_CUDA(cudaStreamSynchronize(s->stream));
+            F2D_CUDA(cudaStreamSynchronize(s->up_stream));
+            F2D_CUDA(cudaStreamSynchronize(s->copy_stream));
+            F2D_CUDA(cudaHostUnregister(const_cast<void*>(host)));
+            s->registered.erase(s->registered.begin() + (ptrdiff_t)i);
+            return F2D_OK;
+        }
+    return F2D_OK;  // not pinned by this solver (e.g. it was page-locked already): nothing to undo
+}
+
+F2D_API int f2d_comm_bytes(const f2d_solver* s, uint64_t* to_up, uint64_t* to_down) {
+    if (!s || !to_up || !to_down) return fail(F2D_ERR_INVALID, "NULL argument");
+    *to_up = s->has_up() ? s->xbytes : 0;
+    *to_down = s->has_down() ? s->xbytes : 0;
+    return F2D_OK;
+}
 
 F2D_API int f2d_upload_field(f2d_solver* s, int field, const float* host) {
     F2D_NEED(s);
@@ -1496,7 +1543,10 @@ F2D_API int f2d_sync(f2d_solver* s) {
     if (s->p2p) {
         unsigned err = 0;
         F2D_CUDA(cudaMemcpy(&err, s->flags + 2, sizeof(unsigned), cudaMemcpyDeviceToHost));
-        if (err) return fail(F2D_ERR_STATE, "halo exchange timed out waiting for a neighbour GPU");
+        if (err) {
+            cudaMemset(s->flags + 2, 0, sizeof(unsigned));  // report once; later exchanges wait normally again
+            return fail(F2D_ERR_STATE, "halo exchange timed out waiting for a neighbour GPU (state invalid since then)");
+        }
     }
     if (s->gs_aux) {
         unsigned err = 0;

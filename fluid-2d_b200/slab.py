@@ -153,3 +153,10 @@ def comm_exchanges(solver):
     n = C.c_uint64()
     capi.check(capi.load().f2d_comm_stats(solver._h, C.byref(n)))
     return int(n.value)
+
+
+def comm_bytes(solver):
+    """Payload bytes this rank has pushed to ONE neighbour so far (f2d_comm_bytes)."""
+    up, down = C.c_uint64(), C.c_uint64()
+    capi.check(capi.load().f2d_comm_bytes(solver._h, C.byref(up), C.byref(down)))
+    return max(int(up.value), int(down.value))

@@ -91,6 +91,16 @@ class FluidSolverB200:
                                           _host(u, True), _host(v, True), _host(u_source), _host(v_source),
                                           viscosity, dt))
 
+    def pin(self, *arrays):
+        """Page-lock caller-owned grids (f2d_pin_host) so that solve() moves them by DMA.  Each array must stay alive
+        and in place until unpin() or close(); solve() never pins behind the caller's back."""
+        for a in arrays:
+            capi.check(self._L.f2d_pin_host(self._h, a.ctypes.data_as(C.c_void_p), a.nbytes))
+
+    def unpin(self, *arrays):
+        for a in arrays:
+            capi.check(self._L.f2d_unpin_host(self._h, a.ctypes.data_as(C.c_void_p)))
+
     # ---- device-resident extension
     def upload(self, density=None, u=None, v=None):
         self._shape_ok(density, u, v)

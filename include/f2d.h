@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define F2D_ABI_VERSION 2
+#define F2D_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define F2D_API __attribute__((visibility("default")))
@@ -121,6 +121,18 @@ F2D_API int f2d_solve_host(f2d_solver* s, float* density, const float* density_s
                    float* u, float* v, const float* u_source, const float* v_source, float viscosity,
                    float dt);
 
+/* Optional: page-lock caller-owned host memory so that f2d_solve_host / f2d_upload / f2d_download move it by DMA
+ * (grid<float> storage is pageable; the reference pays the driver's staged copy on every call,
+ * src/utilities.hpp:57-67).  LIFETIME CONTRACT: [host, host + bytes) must stay allocated and unmoved until
+ * f2d_unpin_host(host) or f2d_destroy.  The library never registers caller memory on its own: freeing a registered
+ * range leaves stale pinned pages behind that a later allocation at the same address would alias.  Memory that is
+ * already page-locked (cudaHostAlloc, torch pin_memory) needs no call.  f2d_unpin_host waits for the solver's
+ * streams first.  (Setting the environment variable F2D_HOST_REGISTER=1 restores round-1 behaviour -- every grid
+ * of >= 1 MiB passed to f2d_solve_host is registered until f2d_destroy -- for callers that accept this contract
+ * for all their grids.) */
+F2D_API int f2d_pin_host(f2d_solver* s, const void* host, size_t bytes);
+F2D_API int f2d_unpin_host(f2d_solver* s, const void* host);
+
 /* ---- device-resident extension (the per-call PCIe copies are the interface's tax) -------- */
 /* copy(m_*_buffer, grid)  (src/utilities.hpp:57-59).  NULL pointers are skipped. */
 F2D_API int f2d_upload(f2d_solver* s, const float* density, const float* u, const float* v);
@@ -174,6 +186,9 @@ F2D_API int f2d_launch_count(const f2d_solver* s, uint64_t* launches);
 F2D_API int f2d_comm_unique_id(char* id128);
 F2D_API int f2d_comm_init(f2d_solver* s, const char* id128, int rank, int nranks, int cfl_cells);
 F2D_API int f2d_comm_stats(const f2d_solver* s, uint64_t* exchanges);
+/* payload bytes this rank has pushed to its upper / lower neighbour so far (halo rows, both directions of the
+ * scatter's reverse exchange included); 0 at a global edge */
+F2D_API int f2d_comm_bytes(const f2d_solver* s, uint64_t* to_up, uint64_t* to_down);
 /* The same slabs with the halo transport replaced by direct NVLink peer stores (f2d_p2p.cu): one kernel
  * per exchange pushes the rows into the neighbour's halo and handshakes through epoch flags in device
  * memory; no NCCL call on the data path.  Every rank exports one 64-byte CUDA IPC handle of its arena plus

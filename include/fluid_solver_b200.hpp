@@ -101,6 +101,11 @@ public:
     void render_velocity_lines(float horizontal_scale, float vertical_scale, float* lines) {
         check(f2d_render_velocity_lines(handle_, horizontal_scale, vertical_scale, lines));
     }
+    // Page-lock a caller-owned grid so that solve() moves it by DMA at PCIe speed instead of through the driver's
+    // staging copy (f2d_pin_host).  The grid must stay alive, and must not be resized, until unpin() or until this
+    // solver is destroyed -- which is why solve() never does this behind the caller's back.
+    void pin(grid<float> const& g) { check(f2d_pin_host(handle_, g.data(), g.rows() * g.cols() * sizeof(float))); }
+    void unpin(grid<float> const& g) { check(f2d_unpin_host(handle_, g.data())); }
     f2d_solver* handle() { return handle_; }
 
 private:

@@ -27,7 +27,7 @@ def test_library_contains_sm100a_code(f2d):
 
 def test_abi_version_and_default_config(f2d):
     L = f2d.load()
-    assert L.f2d_abi_version() == 2
+    assert L.f2d_abi_version() == 3
     cfg = f2d.SolverConfig()
     assert L.f2d_config_default(C.byref(cfg), 256, 256) == 0
     assert cfg.struct_size == C.sizeof(f2d.SolverConfig)

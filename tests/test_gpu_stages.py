@@ -62,6 +62,27 @@ def test_diffuse_fp32_corrected_divide_within_1ulp(f2d, sfo, gpu_ok, mode, T):
                          max_ulp=2, rel_l2=1e-7, max_frac=1e-4)
 
 
+@pytest.mark.parametrize("mode,T", [(NAIVE, 1), (STREAM, 1), (STREAM, 8)], ids=["naive", "stream1", "stream8"])
+@pytest.mark.parametrize("a", [1.7e5, 2.7e6, 1.07e7, 4.3e7])
+def test_diffuse_fp32_corrected_divide_at_the_published_coefficients(f2d, sfo, gpu_ok, mode, T, a):
+    """The diffusion coefficient a = dt * N^2 * rate of the configurations the numbers are published for:
+    1.7e5 (4096^2), 2.7e6 (16384^2), 1.07e7 (32768^2; c = 1 + 4a no longer fits 24 bits, so the ch + cl split of
+    the divisor matters) and 4.3e7 beyond.  f2d_stage_diffuse takes the rate, so a 256^2 grid reproduces each of
+    them.  Against the reference's fp64 divide after 20 sweeps: <= 2 ulp per cell, rel-L2 <= 1e-7, at most 1 cell
+    in 10^4 different at all."""
+    n = 256
+    rate = a / (DT * n * n)
+    assert abs(float(sfo.lib().sfo_diffuse_coeff(n, n, rate, DT)) / a - 1) < 1e-3
+    d, u, v, *_ = rng_fields(n, 78)
+    with make(f2d, n, mode, T, DIV_F32) as s:
+        for fld, kind in ((D, 0), (U, 1), (V, 2)):
+            s.upload(d, u, v)
+            s.stage_diffuse(fld, kind, rate, DT, 20)
+            e = assert_close(s.download()[fld], sfo.diffuse((d, u, v)[fld], kind, rate, DT, 20), "a=%g kind=%d" % (a, kind),
+                             max_ulp=2, rel_l2=1e-7, max_frac=1e-4)
+            print("fp32-corrected divide a=%g kind=%d T=%d: %r" % (a, kind, T, e))
+
+
 @pytest.mark.parametrize("mode,T", RELAX_MODES, ids=RELAX_IDS)
 @pytest.mark.parametrize("n", [8, 64, 132, 260])
 def test_project_bitwise(f2d, sfo, gpu_ok, mode, T, n):

@@ -193,3 +193,29 @@ def test_headless_renderers_match_restatement(f2d, gpu_ok):
     assert np.array_equal(ln[:, :, 0], sx) and np.array_equal(ln[:, :, 1], sy)
     assert_bitwise(np.ascontiguousarray(ln[:, :, 2]), ex, "line end x")
     assert_bitwise(np.ascontiguousarray(ln[:, :, 3]), ey, "line end y")
+
+
+def test_full_step_at_the_headline_config_vs_live_reference_gpu(f2d, gpu_ok):
+    """BASELINE configs[2], the configuration bench.py's headline is quoted on: 4096^2, Kd = Kp = 80, canonical
+    fields, one full step against the UNMODIFIED fluid_solver_gpu run live with the same iteration counts
+    (stage sequence of src/fluid_solver_gpu.cu:236-252 through oracle/ref_gpu_shim.cu).
+      * F2D_DIV_F64: u and v bit-identical; density within the atomic-order tolerance (rel-L2 <= 2e-6,
+        max-abs <= 2e-5 * max(1, |d|max));
+      * product defaults (fp32-corrected divide, a = 1.7e5 here): every field within rel-L2 <= 2e-6,
+        max-abs <= 2e-5 * max(1, |f|max) per step."""
+    from oracle import refs
+    from tools import canonical
+
+    if not refs.have_gpu():
+        pytest.skip("oracle/_ref/libref_gpu.so did not travel to this box")
+    n, k = 4096, 80
+    f = canonical.fields(n)
+    rd, ru, rv, _ = refs.ref_gpu().step_k(f[0], f[3], DIFFUSION_RATE, f[1], f[2], f[4], f[5], VISCOSITY, DT, k, k, True, 1)
+    gd, gu, gv = run_steps(f2d, f, k, k, 1, divide_mode=DIV_F64)
+    assert_bitwise(gu, ru, "u (fp64 divide)")
+    assert_bitwise(gv, rv, "v (fp64 divide)")
+    assert_close(gd, rd, "d (fp64 divide)", rel_l2=D_REL_L2, max_abs_rel=D_MAX_ABS)
+    pd, pu, pv = run_steps(f2d, f, k, k, 1)
+    for name, a, b in (("d", pd, rd), ("u", pu, ru), ("v", pv, rv)):
+        e = assert_close(a, b, "default %s" % name, rel_l2=2e-6, max_abs_rel=2e-5)
+        print("4096^2 K=80 default config vs fluid_solver_gpu: %s %r" % (name, e))
