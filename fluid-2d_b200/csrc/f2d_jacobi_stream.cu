@@ -30,6 +30,19 @@
 //     writes them, gpu.cu:15-23).
 //   * Arithmetic is spelled with intrinsics (f2d_common.cuh) so every level is bit-identical to
 //     one sweep of the naive kernel: T fused sweeps == T single sweeps, bitwise.
+//   * The relaxation itself is issued as PACKED fp32x2 instructions (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2,
+//     new on sm_100): a lane keeps its four columns (x, y, z, w) as the two register pairs A = (x, z) and B = (y, w).
+//     With that pairing every operand of a packed operation is an aligned pair already: north / south / rhs are the
+//     same pair of another row, the east neighbours of A are B, the west neighbours of B are A; only the west
+//     neighbours of A = (left lane's w, y) and the east neighbours of B = (z, right lane's x) are assembled, one
+//     shuffle + one move each.  Each half of a packed operation is the IEEE operation of the scalar kernel, so the
+//     bits do not change; the instruction count per row and level drops from 28 to 17 (pressure) and from 39 to 23
+//     (diffuse).  FADD2 occupies the FMA pipe for two cycles (profiles/ubench_fp32x2_r02.jsonl): what is won are
+//     issue slots, which is what bound the scalar kernel (profiles/ncu_jacobi_*_T8_r01_final.md).  Right-hand-side
+//     rows are re-written in the smem ring in (x, z, y, w) order once when they land, so that every later read is
+//     one 16-byte load straight into two pairs.
+//   * The edge-column fix (columns 0 / N-1 = +/- their neighbour) is compiled only into the variant run by the two
+//     strips that hold a domain edge column (template parameter EDGE, warp-uniform choice outside the row loop).
 //   * The row loop is unrolled by RS (a multiple of 3) so that all window/ring register indices
 //     are compile-time constants; a row step is one basic block; blocks of RS rows in which no
 //     level meets a GLOBAL edge row take a FAST path without range or edge-row checks.
@@ -99,27 +112,134 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// ---- packed fp32x2 values: two floats in one aligned 64-bit register pair (lo | hi << 32)
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo_of(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return a;
+}
+__device__ __forceinline__ float hi_of(f2 v) {
+    float a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+    return b;
+}
+// each half is the IEEE round-to-nearest operation of the scalar kernel (no flush-to-zero, no contraction)
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// one row of a lane: its four columns (x, y, z, w) held as A = (x, z), B = (y, w)
+struct P {
+    f2 A, B;
+};
+__device__ __forceinline__ P perm(const float4& v) {
+    P p;
+    p.A = pk(v.x, v.z);
+    p.B = pk(v.y, v.w);
+    return p;
+}
+__device__ __forceinline__ float4 unperm(const P& p) { return make_float4(lo_of(p.A), lo_of(p.B), hi_of(p.A), hi_of(p.B)); }
+__device__ __forceinline__ P zero_p() {
+    P p;
+    p.A = p.B = 0ull;
+    return p;
+}
+// a ring slot that holds a row in (x, z, y, w) order: 16 bytes <-> two pairs
+__device__ __forceinline__ P lds_p(unsigned smem_addr) {
+    P p;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];\n" : "=l"(p.A), "=l"(p.B) : "r"(smem_addr) : "memory");
+    return p;
+}
+__device__ __forceinline__ void sts_p(unsigned smem_addr, const P& p) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};\n" ::"r"(smem_addr), "l"(p.A), "l"(p.B) : "memory");
+}
+
+// the coefficients of one relaxation, broadcast into pairs
+struct Coef2 {
+    f2 a, rc, nch, ncl;  // diffuse: a, RN32(1/c), -ch, -cl (c = ch + cl)
+    f2 q;                // pressure: 0.25
+    DiffuseCoef s;       // scalar copy (fp64-divide mode)
+};
+__device__ __forceinline__ Coef2 make_coef2(const DiffuseCoef& k) {
+    Coef2 c;
+    c.a = pk(k.a, k.a);
+    c.rc = pk(k.rc, k.rc);
+    c.nch = pk(-k.ch, -k.ch);
+    c.ncl = pk(-k.cl, -k.cl);
+    c.q = pk(0.25f, 0.25f);
+    c.s = k;
+    return c;
+}
+
+// diffuse_iteration_kernel (src/fluid_solver_gpu.cu:81-82) for two cells, fp32-corrected divide; the same operations as
+// diffuse_update<F2D_DIV_F32_CORR> (f2d_common.cuh): FMA(-q0, ch, num) == FMA(q0, -ch, num) exactly
+__device__ __forceinline__ f2 diffuse2(f2 w, f2 e, f2 n, f2 sth, f2 x0, const Coef2& k) {
+    const f2 sum = add2(add2(add2(w, e), n), sth);
+    const f2 num = fma2(k.a, sum, x0);
+    const f2 q0 = mul2(num, k.rc);
+    f2 r = fma2(q0, k.nch, num);
+    r = fma2(q0, k.ncl, r);
+    return fma2(r, k.rc, q0);
+}
+// p_iteration_kernel (src/fluid_solver_gpu.cu:187-188) for two cells
+__device__ __forceinline__ f2 pressure2(f2 dv, f2 e, f2 w, f2 sth, f2 n, f2 quarter) {
+    return mul2(add2(add2(add2(add2(dv, e), w), sth), n), quarter);
+}
+
+// level s+1 row from the level-s rows a (north), b (centre), c (south); l / rt = the cells left of x / right of w
 template <bool DIFFUSE, int DIVMODE>
-__device__ __forceinline__ float4 relax_row(const float4& a, const float4& b, const float4& c, float l, float rt,
-                                            const float4& rhs, const DiffuseCoef& k) {
-    float4 o;
+__device__ __forceinline__ P relax_row(const P& a, const P& b, const P& c, float l, float rt, const P& rhs, const Coef2& k) {
+    P o;
+    if (DIFFUSE && DIVMODE == F2D_DIV_F64) {  // the reference's fp64 divide: scalar
+        const float4 av = unperm(a), bv = unperm(b), cv = unperm(c), rv = unperm(rhs);
+        float4 ov;
+        ov.x = diffuse_update<F2D_DIV_F64>(l, bv.y, av.x, cv.x, rv.x, k.s);
+        ov.y = diffuse_update<F2D_DIV_F64>(bv.x, bv.z, av.y, cv.y, rv.y, k.s);
+        ov.z = diffuse_update<F2D_DIV_F64>(bv.y, bv.w, av.z, cv.z, rv.z, k.s);
+        ov.w = diffuse_update<F2D_DIV_F64>(bv.z, rt, av.w, cv.w, rv.w, k.s);
+        return perm(ov);
+    }
+    const f2 WL = pk(l, lo_of(b.B));   // west of (x, z) = (left lane's w, y)
+    const f2 ER = pk(hi_of(b.A), rt);  // east of (y, w) = (z, right lane's x)
     if (DIFFUSE) {
-        o.x = diffuse_update<DIVMODE>(l, b.y, a.x, c.x, rhs.x, k);
-        o.y = diffuse_update<DIVMODE>(b.x, b.z, a.y, c.y, rhs.y, k);
-        o.z = diffuse_update<DIVMODE>(b.y, b.w, a.z, c.z, rhs.z, k);
-        o.w = diffuse_update<DIVMODE>(b.z, rt, a.w, c.w, rhs.w, k);
+        o.A = diffuse2(WL, b.B, a.A, c.A, rhs.A, k);
+        o.B = diffuse2(b.A, ER, a.B, c.B, rhs.B, k);
     } else {
-        o.x = pressure_update(rhs.x, b.y, l, c.x, a.x);
-        o.y = pressure_update(rhs.y, b.z, b.x, c.y, a.y);
-        o.z = pressure_update(rhs.z, b.w, b.y, c.z, a.z);
-        o.w = pressure_update(rhs.w, rt, b.z, c.w, a.w);
+        o.A = pressure2(rhs.A, b.B, WL, c.A, a.A, k.q);
+        o.B = pressure2(rhs.B, ER, b.A, c.B, a.B, k.q);
     }
     return o;
 }
 
+// domain edge columns of an interior row: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32)
+__device__ __forceinline__ P fix_edge_cols(const P& v, bool has_left, bool has_right, bool neg) {
+    float4 f = unperm(v);
+    f.x = has_left ? apply_sign(f.y, neg) : f.x;
+    f.w = has_right ? apply_sign(f.z, neg) : f.w;
+    return perm(f);
+}
+
 // edge row from the adjacent interior row of the same level; corner cells keep `keep`
-__device__ __forceinline__ float4 edge_row(const float4& inner, const float4& keep, bool neg, bool has_left,
-                                           bool has_right) {
+__device__ __forceinline__ P edge_row(const P& inner_p, const P& keep_p, bool neg, bool has_left, bool has_right) {
+    const float4 inner = unperm(inner_p), keep = unperm(keep_p);
     float4 o;
     o.x = apply_sign(inner.x, neg);
     o.y = apply_sign(inner.y, neg);
@@ -127,7 +247,7 @@ __device__ __forceinline__ float4 edge_row(const float4& inner, const float4& ke
     o.w = apply_sign(inner.w, neg);
     if (has_left) o.x = keep.x;
     if (has_right) o.w = keep.w;
-    return o;
+    return perm(o);
 }
 
 // per-warp constants of one (strip, chunk)
@@ -141,7 +261,7 @@ struct Ctx {
     float* aux;       // fused divergence: the divergence field written for the later passes
     float mhalf_h;    // fused divergence: -0.5f * h; fused add_sources: dt
     int row_top, row_bot;  // local index of the global top / bottom edge row (or out of range)
-    DiffuseCoef coef;
+    Coef2 coef;
     int pitch, rs, re, y0, y1;
     int cp_bytes;
     bool top_dom, bot_dom, own_x, has_left, has_right, edge_warp, neg_c, neg_r;
@@ -155,9 +275,9 @@ struct Ctx {
 // feed cells outside the dependency cone of the rows this warp stores, and the store itself is
 // predicated on the owned row range.  Only blocks in which a level meets a GLOBAL top or bottom edge
 // row (edge rule, corner carry) take the checked path (FAST == false).
-template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool FAST, int RS, int RINGR, int NRH>
-__device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, float4 (&W)[T][3], float4 (&RH)[NRH],
-                                          float4& out_prev, float (&wl)[T], float (&er)[T], float4 (&UV)[2][3]) {
+template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool FAST, bool EDGE, int RS, int RINGR, int NRH>
+__device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, P (&W)[T][3], P (&RH)[NRH],
+                                          P& out_prev, float (&wl)[T], float (&er)[T], float4 (&UV)[2][3]) {
     // PIN_ZERO == 2: the first pressure pass with the divergence fused in (gpu.cu:164-177 + :376): the two
     // async rings carry u and v rows instead of iterate and rhs; the rhs row r-1 is computed on the fly
     constexpr bool FUSE = (PIN_ZERO == 2);
@@ -194,22 +314,28 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
                 x0.y = row_in ? __fmaf_rn(cx.mhalf_h, s4.y, f4.y) : f4.y;
                 x0.z = row_in ? __fmaf_rn(cx.mhalf_h, s4.z, f4.z) : f4.z;
                 x0.w = (row_in && !cx.has_right) ? __fmaf_rn(cx.mhalf_h, s4.w, f4.w) : f4.w;
-                W[0][m3(k)] = x0;
+                const P x0p = perm(x0);
+                W[0][m3(k)] = x0p;
                 if (RHS_REGS)
-                    RH[mrs(k, RS)] = x0;
+                    RH[mrs(k, RS)] = x0p;
                 else
-                    sts128((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sd, x0);
+                    sts_p((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sd, x0p);
                 if (cx.own_x && r >= cx.y0 && r < cx.y1 && r <= cx.re) st_global_f4(cx.aux + (size_t)r * cx.pitch, x0);
             } else if (!PIN_ZERO)
-                W[0][m3(k)] = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);
+                W[0][m3(k)] = perm(lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp));
             else
-                W[0][m3(k)] = make_float4(0.f, 0.f, 0.f, 0.f);
+                W[0][m3(k)] = zero_p();
             if (FSRC) {
             } else if (FUSE) {
                 UV[0][m3(k)] = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);  // u row r
                 UV[1][m3(k)] = lds128((((unsigned)r << 9) & MASKR) | cx.sr);                // v row r
             } else if (RHS_REGS) {
-                RH[mrs(k, RS)] = lds128((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sr);
+                RH[mrs(k, RS)] = perm(lds128((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sr));
+            } else {
+                // the rhs row just landed in (x, y, z, w) order: re-write it as (x, z, y, w) so that each of its T
+                // later reads is one 16-byte load into two aligned pairs (every lane touches only its own 16 bytes)
+                const unsigned slot = (((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sr;
+                sts_p(slot, perm(lds128(slot)));
             }
         }
         if (FUSE) {
@@ -227,9 +353,9 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
             dv.w = cx.has_right ? dv.z : dv.w;
             const int qd = r - 1;
             if (RHS_REGS)
-                RH[mrs(k - 1, RS)] = dv;
+                RH[mrs(k - 1, RS)] = perm(dv);
             else
-                sts128((((unsigned)qd << 9) & ((RINGR - 1) << 9)) | cx.sd, dv);
+                sts_p((((unsigned)qd << 9) & ((RINGR - 1) << 9)) | cx.sd, perm(dv));
             if (cx.own_x && qd >= cx.rs + 1 && qd <= cx.re - 1) {
                 if (qd >= cx.y0 && qd < cx.y1) st_global_f4(cx.aux + (size_t)qd * cx.pitch, dv);
                 // the edge rows of the stored field copy the adjacent interior row, corners are the memset zeros
@@ -244,9 +370,9 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
         // west/east neighbours of the centre rows of all levels (rows produced in the previous step)
 #pragma unroll
         for (int s = 0; s < T; ++s) {
-            const float4 bb = W[s][m3(k - s - 1)];
-            wl[s] = __shfl_up_sync(0xffffffffu, bb.w, 1);
-            er[s] = __shfl_down_sync(0xffffffffu, bb.x, 1);
+            const P bb = W[s][m3(k - s - 1)];
+            wl[s] = __shfl_up_sync(0xffffffffu, hi_of(bb.B), 1);    // the left lane's w
+            er[s] = __shfl_down_sync(0xffffffffu, lo_of(bb.A), 1);  // the right lane's x
         }
 #endif
 
@@ -262,39 +388,37 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
             const int sa = m3(k - s - 2), sm = m3(k - s - 1), sc = m3(k - s);
             const int sn = (s + 1 < T) ? s + 1 : 0;  // keeps the dead branch's index in range
             if (FAST || (s >= s_lo && s <= s_hi)) {
-                const float4 a = W[s][sa], b = W[s][sm], c = W[s][sc];
+                const P a = W[s][sa], b = W[s][sm], c = W[s][sc];
                 const float l = wl[s], rt = er[s];
-                float4 rhs;
+                P rhs;
                 if (RHS_REGS)
                     rhs = RH[mrs(k - s - 1, RS)];
                 else
-                    rhs = lds128((((unsigned)q << 9) & ((RINGR - 1) << 9)) | ((FUSE || FSRC) ? cx.sd : cx.sr));
-                float4 nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
-                // interior rows: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32).  Written as
-                // two predicated selects (no branch) so that a whole row step stays one basic block and
-                // the scheduler can overlap the tail of one level with the head of the next.
-                nw.x = cx.has_left ? apply_sign(nw.y, cx.neg_c) : nw.x;
-                nw.w = cx.has_right ? apply_sign(nw.z, cx.neg_c) : nw.w;
+                    rhs = lds_p((((unsigned)q << 9) & ((RINGR - 1) << 9)) | ((FUSE || FSRC) ? cx.sd : cx.sr));
+                P nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
+                // only the strips that hold a domain edge column run this variant; branch-free selects, so a whole
+                // row step stays one basic block
+                if (EDGE) nw = fix_edge_cols(nw, cx.has_left, cx.has_right, cx.neg_c);
                 if (s + 1 < T) {
                     W[sn][sm] = nw;
                 } else {
                     out_prev = nw;
-                    if (cx.own_x && q >= cx.y0 && q < cx.y1) st_global_f4(cx.next + (size_t)q * cx.pitch, nw);
+                    if (cx.own_x && q >= cx.y0 && q < cx.y1) st_global_f4(cx.next + (size_t)q * cx.pitch, unperm(nw));
                 }
                 if (!FAST && s == s_top) {  // global top edge row of the same level (corners kept)
-                    const float4 e = edge_row(nw, a, cx.neg_r, cx.has_left, cx.has_right);
+                    const P e = edge_row(nw, a, cx.neg_r, cx.has_left, cx.has_right);
                     if (s + 1 < T)
                         W[sn][sa] = e;
                     else if (cx.own_x && cx.y0 == 0)
-                        st_global_f4(cx.next, e);
+                        st_global_f4(cx.next, unperm(e));
                 }
             } else if (!FAST && s == s_bot && q >= cx.rs + 1) {  // global bottom edge row
-                const float4 inner = (s + 1 < T) ? W[sn][sa] : out_prev;
-                const float4 e = edge_row(inner, W[s][sm], cx.neg_r, cx.has_left, cx.has_right);
+                const P inner = (s + 1 < T) ? W[sn][sa] : out_prev;
+                const P e = edge_row(inner, W[s][sm], cx.neg_r, cx.has_left, cx.has_right);
                 if (s + 1 < T)
                     W[sn][sm] = e;
                 else if (cx.own_x && q >= cx.y0 && q < cx.y1)
-                    st_global_f4(cx.next + (size_t)q * cx.pitch, e);
+                    st_global_f4(cx.next + (size_t)q * cx.pitch, unperm(e));
             }
         }
         // 4. the centre row of level s in the NEXT step is row r - s (slot m3(k - s)); it is final now,
@@ -302,9 +426,9 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, flo
 #if F2D_SHFL_AHEAD
 #pragma unroll
         for (int s = 0; s < T; ++s) {
-            const float4 b = W[s][m3(k - s)];
-            wl[s] = __shfl_up_sync(0xffffffffu, b.w, 1);
-            er[s] = __shfl_down_sync(0xffffffffu, b.x, 1);
+            const P b = W[s][m3(k - s)];
+            wl[s] = __shfl_up_sync(0xffffffffu, hi_of(b.B), 1);
+            er[s] = __shfl_down_sync(0xffffffffu, lo_of(b.A), 1);
         }
 #endif
     }
@@ -341,7 +465,7 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
 
     const RelaxField& fld = batch.f[blockIdx.y];
     Ctx cx;
-    cx.coef = fld.coef;
+    cx.coef = make_coef2(fld.coef);
     cx.neg_c = (fld.kind == F2D_BND_OPPOSITE_HORIZONTAL);
     cx.neg_r = (fld.kind == F2D_BND_OPPOSITE_VERTICAL);
     cx.pitch = g.pitch;
@@ -400,9 +524,9 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     const int top_lo = cx.top_dom ? 2 : 1 << 30, top_hi = cx.top_dom ? T + 1 : -1;
     const int bot_lo = cx.bot_dom ? cx.re + 1 : 1 << 30, bot_hi = cx.bot_dom ? cx.re + T : -1;
 
-    float4 W[T][3];
-    float4 RH[NRH];
-    float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
+    P W[T][3];
+    P RH[NRH];
+    P out_prev = zero_p();
     float wl[T], er[T];
     float4 UV[2][3];
 #pragma unroll
@@ -411,10 +535,10 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     for (int s = 0; s < T; ++s) {
         wl[s] = er[s] = 0.f;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) W[s][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = 0; m < 3; ++m) W[s][m] = zero_p();
     }
 #pragma unroll
-    for (int m = 0; m < NRH; ++m) RH[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < NRH; ++m) RH[m] = zero_p();
 
     // ---- prologue: rows rs .. rs+PFD-1 in flight
 #pragma unroll
@@ -428,13 +552,25 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
         cp_async_commit();
     }
 
-    for (int rb = 0; rb < nsteps; rb += RS) {
-        const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
-        const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
-        if (!edge_block)
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
-        else
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
+    // the edge-column variant is chosen once per warp (warp-uniform), outside the row loop
+    if (!cx.edge_warp) {
+        for (int rb = 0; rb < nsteps; rb += RS) {
+            const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
+            const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
+            if (!edge_block)
+                run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
+            else
+                run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
+        }
+    } else {
+        for (int rb = 0; rb < nsteps; rb += RS) {
+            const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
+            const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
+            if (!edge_block)
+                run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
+            else
+                run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
+        }
     }
     cp_async_wait<0>();
 }
@@ -444,7 +580,8 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
 // with c_class the instruction count of one row step (interior strip : edge strip ~ 1 : kEdgeStripCost,
 // read off the SASS).  The largest chunk heights whose warp count fits the resident slots are found
 // by bisection on the common cost.  First/last chunks are trimmed by the cost of their checked steps.
-constexpr double kEdgeStripCost = 1.0;   // edge strips cost the same since the edge-column fix is branch-free
+constexpr double kEdgeStripCost = 1.35;  // default cost of an edge strip's row step relative to an interior strip's (SASS count;
+                                         // only the edge strips carry the edge-column fix); F2D_STREAM_EDGE_COST_PCT overrides
 constexpr double kCheckedStepCost = 3.4; // checked (global edge row) step relative to a fast step
 
 struct ClassPlan {
@@ -471,22 +608,29 @@ inline ClassPlan plan_class(int rows, int T, int RS, double cost_budget, double 
 }
 
 template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, int MINB>
-void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, int sm_count, cudaStream_t st) {
+cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, int sm_count, cudaStream_t st) {
     auto kern = k_jacobi_stream<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, MINB>;
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;
     int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
     wpc = std::min(wpc, 4);  // __launch_bounds__(128, ...)
     const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS) + (PIN_ZERO >= 2 ? kRingP : 0)) * kLanes * sizeof(float4) +
                         (size_t)ring_r_of(T, RHS_REGS) * kLanes * sizeof(float4);  // alignment slack
-    // per device (function attributes live in the device's context) and per CTA size
+    // per device (function attributes live in the device's context) and per CTA size; a failed opt-in to more than
+    // 48 KB of dynamic shared memory or a failed occupancy query is reported here, not at some later launch
     static int occ_cache_dev[16][9] = {};
     int dev = 0;
-    cudaGetDevice(&dev);
+    cudaError_t err = cudaGetDevice(&dev);
+    if (err != cudaSuccess) return err;
     int* occ_cache = occ_cache_dev[dev & 15];
     if (occ_cache[wpc] == 0) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024) {
+            err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (err != cudaSuccess) return err;
+        }
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem) != cudaSuccess || occ < 1) occ = 1;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, wpc * 32, smem);
+        if (err != cudaSuccess) return err;
+        if (occ < 1) return cudaErrorLaunchOutOfResources;
         occ_cache[wpc] = occ;
     }
     StreamPlan plan;
@@ -497,17 +641,18 @@ void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, in
     const bool both_edges = (g.grow0 == 0 && g.grow0 + g.rows == g.grows);
     const long slots = (long)occ_cache[wpc] * sm_count * wpc / b.n;  // warps available per field
     const int min_mult = tune.min_chunk_mult > 0 ? tune.min_chunk_mult : 2;  // profiles/tune_small_r01.log
+    const double edge_cost = tune.edge_cost_pct > 0 ? tune.edge_cost_pct / 100.0 : kEdgeStripCost;
     ClassPlan ci = {0, 0, 0}, ce = {0, 0, 0};
     if (tune.chunk_rows > 0) {  // manual override: same height for both classes, no trimming
         ci.chunk_rows = ce.chunk_rows = std::min(tune.chunk_rows, g.rows);
         ci.chunks = ce.chunks = (g.rows + ci.chunk_rows - 1) / ci.chunk_rows;
     } else {
         // smallest common cost whose warp count fits the resident slots
-        double lo = 4.0 * T, hi = (double)(g.rows + 2 * T) * kEdgeStripCost + 1.0;
+        double lo = 4.0 * T, hi = (double)(g.rows + 2 * T) * edge_cost + 1.0;
         for (int it = 0; it < 40; ++it) {
             const double mid = 0.5 * (lo + hi);
             const ClassPlan a = plan_class(g.rows, T, RS, mid, 1.0, both_edges, min_mult);
-            const ClassPlan e = plan_class(g.rows, T, RS, mid, kEdgeStripCost, both_edges, min_mult);
+            const ClassPlan e = plan_class(g.rows, T, RS, mid, edge_cost, both_edges, min_mult);
             const long warps = (long)n_int * a.chunks + (long)plan.n_edge_strips * e.chunks;
             if (warps <= slots)
                 hi = mid;
@@ -515,7 +660,7 @@ void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, in
                 lo = mid;
         }
         ci = plan_class(g.rows, T, RS, hi, 1.0, both_edges, min_mult);
-        ce = plan_class(g.rows, T, RS, hi, kEdgeStripCost, both_edges, min_mult);
+        ce = plan_class(g.rows, T, RS, hi, edge_cost, both_edges, min_mult);
     }
     plan.chunks[0] = ci.chunks;
     plan.chunk_rows[0] = ci.chunk_rows;
@@ -527,29 +672,25 @@ void launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, in
     const long total_warps = (long)plan.warps_int + (long)plan.n_edge_strips * ce.chunks;
     dim3 grid((unsigned)((total_warps + wpc - 1) / wpc), b.n);
     kern<<<grid, wpc * 32, smem, st>>>(g, b, plan);
+    return cudaGetLastError();
 }
 
 template <int T, bool RHS_REGS, int MINB>
-void launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, const StreamTuning& tune, int sm_count,
-              cudaStream_t st) {
+cudaError_t launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, const StreamTuning& tune, int sm_count,
+                     cudaStream_t st) {
     if (!diffuse) {
         if (b.f[0].aux != nullptr)  // first pressure pass with the divergence fused in: prev = u, rhs = v
-            launch_one<T, false, F2D_DIV_F64, 2, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-        else if (b.f[0].prev == nullptr)
-            launch_one<T, false, F2D_DIV_F64, 1, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-        else
-            launch_one<T, false, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-    } else if (divmode == F2D_DIV_F64) {
-        if (b.f[0].aux != nullptr)  // first diffuse pass with add_sources fused in: prev = field, rhs = source
-            launch_one<T, true, F2D_DIV_F64, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-        else
-            launch_one<T, true, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-    } else {
-        if (b.f[0].aux != nullptr)
-            launch_one<T, true, F2D_DIV_F32_CORR, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-        else
-            launch_one<T, true, F2D_DIV_F32_CORR, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+            return launch_one<T, false, F2D_DIV_F64, 2, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        if (b.f[0].prev == nullptr) return launch_one<T, false, F2D_DIV_F64, 1, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        return launch_one<T, false, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     }
+    if (divmode == F2D_DIV_F64) {
+        if (b.f[0].aux != nullptr)  // first diffuse pass with add_sources fused in: prev = field, rhs = source
+            return launch_one<T, true, F2D_DIV_F64, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        return launch_one<T, true, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+    }
+    if (b.f[0].aux != nullptr) return launch_one<T, true, F2D_DIV_F32_CORR, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+    return launch_one<T, true, F2D_DIV_F32_CORR, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
 }
 
 }  // namespace
@@ -559,31 +700,17 @@ bool stream_supported(const Geom& g, int T) {
     return g.cols >= 4 && (g.cols % 4 == 0) && (g.pitch % 4 == 0) && g.rows >= 3;
 }
 
-void launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
-                          const StreamTuning& tune, int sm_count, cudaStream_t st) {
+cudaError_t launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
+                                 const StreamTuning& tune, int sm_count, cudaStream_t st) {
     (void)sweeps;  // == T: the step driver decomposes K into passes of 8/4/2/1 sweeps
     // T = 8 keeps the right-hand side in the smem ring (unroll 3): with a register ring the unrolled
-    // row loop (9 x 8 levels) outgrows the instruction cache.  min_blocks picks the register budget
-    // (resident 128-thread CTAs per SM): T = 8 -> 3 (168 regs) or 2, T = 4 -> 4 (128 regs) or 5.
-    const bool rr = (tune.rhs_in_smem == 0) && T < 8;
-    const int mb = tune.min_blocks;
+    // row loop (9 x 8 levels) outgrows the instruction cache.  MINB = resident 128-thread CTAs per SM the register
+    // allocator must allow: T = 8 -> 3 (168 regs), T = 4 -> 4 (128 regs).
     switch (T) {
-        case 1: launch_T<1, true, 6>(g, b, diffuse, divmode, tune, sm_count, st); break;
-        case 2: launch_T<2, true, 6>(g, b, diffuse, divmode, tune, sm_count, st); break;
-        case 4:
-            if (rr)
-                launch_T<4, true, 4>(g, b, diffuse, divmode, tune, sm_count, st);
-            else if (mb == 5)
-                launch_T<4, false, 5>(g, b, diffuse, divmode, tune, sm_count, st);
-            else
-                launch_T<4, false, 4>(g, b, diffuse, divmode, tune, sm_count, st);
-            break;
-        default:
-            if (mb == 2)
-                launch_T<8, false, 2>(g, b, diffuse, divmode, tune, sm_count, st);
-            else
-                launch_T<8, false, 3>(g, b, diffuse, divmode, tune, sm_count, st);
-            break;
+        case 1: return launch_T<1, true, 6>(g, b, diffuse, divmode, tune, sm_count, st);
+        case 2: return launch_T<2, true, 6>(g, b, diffuse, divmode, tune, sm_count, st);
+        case 4: return launch_T<4, true, 4>(g, b, diffuse, divmode, tune, sm_count, st);
+        default: return launch_T<8, false, 3>(g, b, diffuse, divmode, tune, sm_count, st);
     }
 }
 

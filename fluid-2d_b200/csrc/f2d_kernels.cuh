@@ -104,14 +104,15 @@ void launch_velocity_to_lines(const Geom& g, const float* u, const float* v, voi
 struct StreamTuning {
     int chunk_rows;     // output rows per warp (0 = auto)
     int warps_per_cta;  // 0 = auto
-    int rhs_in_smem;    // 0 = rhs rows ride in a register ring (default), 1 = re-read from the smem ring
-    int min_blocks;     // 0 = default register budget; see launch_jacobi_stream
+    int rhs_in_smem;    // unused since round 2 (T <= 4: register ring, T = 8: smem ring)
+    int min_blocks;     // unused since round 2
     int min_chunk_mult; // chunks own at least min_chunk_mult * T rows (0 = 2)
+    int edge_cost_pct;  // cost of an edge strip's row step in percent of an interior strip's (0 = default)
 };
 // `sweeps` (1..T) Jacobi sweeps in one pass over the field(s); returns false if (T, geometry)
 // is not supported by the streaming kernel.
 bool stream_supported(const Geom& g, int T);
-void launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
-                          const StreamTuning& tune, int sm_count, cudaStream_t st);
+cudaError_t launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
+                                 const StreamTuning& tune, int sm_count, cudaStream_t st);
 
 }  // namespace f2d

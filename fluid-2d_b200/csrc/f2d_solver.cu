@@ -84,7 +84,7 @@ struct f2d_solver {
     GraphKey graph_key = {0.f, 0.f, 0.f, false};
     uint64_t graph_kernels = 0;  // kernel launches inside one replay of the graph
     uint64_t launches = 0;       // kernel launches issued so far (graph nodes included)
-    StreamTuning tune = {0, 0, 0, 0, 0};
+    StreamTuning tune = {0, 0, 0, 0, 0, 0};
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // solve(): the density field is final long before the velocity projections finish; it is copied
@@ -292,9 +292,10 @@ struct f2d_solver {
                 b.f[i].kind = kinds[i];
                 b.f[i].coef = coefs ? coefs[i] : DiffuseCoef{0.f, 0.f, 0.f, 0.f, 1.0};
             }
-            if (stream_mode)
-                launch_jacobi_stream(g, b, diffuse, (int)cfg.divide_mode, (int)T, (int)T, tune, sm_count, stream);
-            else
+            if (stream_mode) {
+                const cudaError_t le = launch_jacobi_stream(g, b, diffuse, (int)cfg.divide_mode, (int)T, (int)T, tune, sm_count, stream);
+                if (le != cudaSuccess) return fail(F2D_ERR_CUDA, "streaming Jacobi pass (T=%u) could not be launched: %s", T, cudaGetErrorString(le));
+            } else
                 launch_jacobi_naive(g, b, diffuse, (int)cfg.divide_mode, stream);
             count();
             for (int i = 0; i < n; ++i) {
@@ -346,7 +347,8 @@ struct f2d_solver {
             b.f[0].aux = dv;
             b.f[0].kind = F2D_BND_CONTINUOUS;
             b.f[0].coef = DiffuseCoef{-0.5f * h(), 0.f, 0.f, 0.f, 1.0};
-            launch_jacobi_stream(g, b, false, (int)cfg.divide_mode, (int)T, (int)T, tune, sm_count, stream);
+            const cudaError_t le = launch_jacobi_stream(g, b, false, (int)cfg.divide_mode, (int)T, (int)T, tune, sm_count, stream);
+            if (le != cudaSuccess) return fail(F2D_ERR_CUDA, "fused divergence + pressure pass (T=%u) could not be launched: %s", T, cudaGetErrorString(le));
             count();
             const int iuv = std::max(get_inv(u_in), get_inv(v_in));
             set_inv(dv, iuv + 1);
@@ -1320,6 +1322,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     s->tune.rhs_in_smem = env_int("F2D_STREAM_RHS_SMEM", 0);
     s->tune.min_blocks = env_int("F2D_STREAM_MIN_BLOCKS", 0);
     s->tune.min_chunk_mult = env_int("F2D_STREAM_MIN_CHUNK_MULT", 0);
+    s->tune.edge_cost_pct = env_int("F2D_STREAM_EDGE_COST_PCT", 0);
     s->fuse_divergence = env_int("F2D_FUSE_DIVERGENCE", 1) != 0;
     s->fuse_sources = env_int("F2D_FUSE_SOURCES", 1) != 0;
 
