@@ -30,19 +30,6 @@
 //     writes them, gpu.cu:15-23).
 //   * Arithmetic is spelled with intrinsics (f2d_common.cuh) so every level is bit-identical to
 //     one sweep of the naive kernel: T fused sweeps == T single sweeps, bitwise.
-//   * The relaxation itself is issued as PACKED fp32x2 instructions (add/mul/fma.rn.f32x2 -> FADD2 / FMUL2 / FFMA2,
-//     new on sm_100): a lane keeps its four columns (x, y, z, w) as the two register pairs A = (x, z) and B = (y, w).
-//     With that pairing every operand of a packed operation is an aligned pair already: north / south / rhs are the
-//     same pair of another row, the east neighbours of A are B, the west neighbours of B are A; only the west
-//     neighbours of A = (left lane's w, y) and the east neighbours of B = (z, right lane's x) are assembled, one
-//     shuffle + one move each.  Each half of a packed operation is the IEEE operation of the scalar kernel, so the
-//     bits do not change; the instruction count per row and level drops from 28 to 17 (pressure) and from 39 to 23
-//     (diffuse).  FADD2 occupies the FMA pipe for two cycles (profiles/ubench_fp32x2_r02.jsonl): what is won are
-//     issue slots, which is what bound the scalar kernel (profiles/ncu_jacobi_*_T8_r01_final.md).  Right-hand-side
-//     rows are re-written in the smem ring in (x, z, y, w) order once when they land, so that every later read is
-//     one 16-byte load straight into two pairs.
-//   * The edge-column fix (columns 0 / N-1 = +/- their neighbour) is compiled only into the variant run by the two
-//     strips that hold a domain edge column (template parameter EDGE, warp-uniform choice outside the row loop).
 //   * The row loop is unrolled by RS (a multiple of 3) so that all window/ring register indices
 //     are compile-time constants; a row step is one basic block; blocks of RS rows in which no
 //     level meets a GLOBAL edge row take a FAST path without range or edge-row checks.
@@ -52,6 +39,18 @@
 //     and writes it out as the right-hand side of the later passes.
 //   * A host planner (launch_one) sizes the chunks from a cost model so that one launch is exactly
 //     one wave of resident warps that finish together.
+//   * The kernel is bound by instruction issue (profiles/ncu_jacobi_*_T8_r01_final.md), so everything that is not one
+//     of the 5 / 8 floating-point operations per cell is kept out of the row loop: the edge-column fix exists only in
+//     the variant run by the two strips that hold a domain edge column (template parameter EDGE, warp-uniform choice
+//     outside the loop); global rows are addressed with running 32-bit element offsets (one add per step); with the
+//     right-hand side in shared memory (T = 8) its ring is MIRRORED -- 16 slots plus a copy of slots 0..7 behind them
+//     -- so that the T rows r-1 .. r-T a step reads are always contiguous below one pointer and every level reads
+//     its row at a compile-time offset from it (no per-level address arithmetic).
+//   * A packed fp32x2 variant (FADD2 / FMUL2 / FFMA2, register pairs (x,z) / (y,w)) was built in round 2 and is
+//     bit-identical too, but slower: 72.4 vs 59.1 us per pressure pass, 89 vs 81 us per diffuse pass under ncu at
+//     4096^2 -- the packed operations occupy the FMA pipe for two cycles each (no pipe time saved,
+//     profiles/ubench_fp32x2_r02.jsonl), pair assembly costs two moves per row and level, and the 168-register
+//     budget spills (git 7a65d0d; profiles/ncu_jacobi_*_T8_r02_packed_fp32x2.md).
 #include <algorithm>
 
 #include "f2d_kernels.cuh"
@@ -75,11 +74,11 @@ __host__ __device__ constexpr int halo_of(int T) { return T <= 4 ? 4 : ((T + 3) 
 __host__ __device__ constexpr int m3(int x) { return ((x % 3) + 3) % 3; }
 __host__ __device__ constexpr int rs_of(int T) { return 3 * ((T + 1 + 2) / 3); }  // rhs register ring
 __host__ __device__ constexpr int mrs(int x, int RS) { return ((x % RS) + RS) % RS; }
-// rhs smem ring slots (power of two): register mode only needs the landing zone,
-// smem mode keeps rows r+PFD .. r-T
-__host__ __device__ constexpr int ring_r_of(int T, bool rhs_regs) {
-    return rhs_regs ? kRingP : ((kPFD + T + 2) <= 8 ? 8 : 16);
-}
+// rhs smem ring: register mode only needs the landing zone (kRingP slots); smem mode keeps rows r+PFD .. r-T in
+// kRingR slots and mirrors slots 0 .. kMirror-1 behind them (see slot_rd)
+constexpr int kRingR = 16;   // >= PFD + T + 2 for T <= 8
+constexpr int kMirror = 8;   // >= T
+__host__ __device__ constexpr int ring_r_slots(bool rhs_regs) { return rhs_regs ? kRingP : kRingR + kMirror; }
 
 // Work decomposition.  Warps fall into two classes with different cost per row: class 0 = interior
 // strips, class 1 = the strips that hold a left/right domain edge column (extra edge fix per level).
@@ -112,134 +111,27 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// ---- packed fp32x2 values: two floats in one aligned 64-bit register pair (lo | hi << 32)
-typedef unsigned long long f2;
-__device__ __forceinline__ f2 pk(float lo, float hi) {
-    f2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float lo_of(f2 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return a;
-}
-__device__ __forceinline__ float hi_of(f2 v) {
-    float a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-    return b;
-}
-// each half is the IEEE round-to-nearest operation of the scalar kernel (no flush-to-zero, no contraction)
-__device__ __forceinline__ f2 add2(f2 a, f2 b) {
-    f2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
-    f2 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
-    f2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
-// one row of a lane: its four columns (x, y, z, w) held as A = (x, z), B = (y, w)
-struct P {
-    f2 A, B;
-};
-__device__ __forceinline__ P perm(const float4& v) {
-    P p;
-    p.A = pk(v.x, v.z);
-    p.B = pk(v.y, v.w);
-    return p;
-}
-__device__ __forceinline__ float4 unperm(const P& p) { return make_float4(lo_of(p.A), lo_of(p.B), hi_of(p.A), hi_of(p.B)); }
-__device__ __forceinline__ P zero_p() {
-    P p;
-    p.A = p.B = 0ull;
-    return p;
-}
-// a ring slot that holds a row in (x, z, y, w) order: 16 bytes <-> two pairs
-__device__ __forceinline__ P lds_p(unsigned smem_addr) {
-    P p;
-    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];\n" : "=l"(p.A), "=l"(p.B) : "r"(smem_addr) : "memory");
-    return p;
-}
-__device__ __forceinline__ void sts_p(unsigned smem_addr, const P& p) {
-    asm volatile("st.shared.v2.b64 [%0], {%1, %2};\n" ::"r"(smem_addr), "l"(p.A), "l"(p.B) : "memory");
-}
-
-// the coefficients of one relaxation, broadcast into pairs
-struct Coef2 {
-    f2 a, rc, nch, ncl;  // diffuse: a, RN32(1/c), -ch, -cl (c = ch + cl)
-    f2 q;                // pressure: 0.25
-    DiffuseCoef s;       // scalar copy (fp64-divide mode)
-};
-__device__ __forceinline__ Coef2 make_coef2(const DiffuseCoef& k) {
-    Coef2 c;
-    c.a = pk(k.a, k.a);
-    c.rc = pk(k.rc, k.rc);
-    c.nch = pk(-k.ch, -k.ch);
-    c.ncl = pk(-k.cl, -k.cl);
-    c.q = pk(0.25f, 0.25f);
-    c.s = k;
-    return c;
-}
-
-// diffuse_iteration_kernel (src/fluid_solver_gpu.cu:81-82) for two cells, fp32-corrected divide; the same operations as
-// diffuse_update<F2D_DIV_F32_CORR> (f2d_common.cuh): FMA(-q0, ch, num) == FMA(q0, -ch, num) exactly
-__device__ __forceinline__ f2 diffuse2(f2 w, f2 e, f2 n, f2 sth, f2 x0, const Coef2& k) {
-    const f2 sum = add2(add2(add2(w, e), n), sth);
-    const f2 num = fma2(k.a, sum, x0);
-    const f2 q0 = mul2(num, k.rc);
-    f2 r = fma2(q0, k.nch, num);
-    r = fma2(q0, k.ncl, r);
-    return fma2(r, k.rc, q0);
-}
-// p_iteration_kernel (src/fluid_solver_gpu.cu:187-188) for two cells
-__device__ __forceinline__ f2 pressure2(f2 dv, f2 e, f2 w, f2 sth, f2 n, f2 quarter) {
-    return mul2(add2(add2(add2(add2(dv, e), w), sth), n), quarter);
-}
-
-// level s+1 row from the level-s rows a (north), b (centre), c (south); l / rt = the cells left of x / right of w
 template <bool DIFFUSE, int DIVMODE>
-__device__ __forceinline__ P relax_row(const P& a, const P& b, const P& c, float l, float rt, const P& rhs, const Coef2& k) {
-    P o;
-    if (DIFFUSE && DIVMODE == F2D_DIV_F64) {  // the reference's fp64 divide: scalar
-        const float4 av = unperm(a), bv = unperm(b), cv = unperm(c), rv = unperm(rhs);
-        float4 ov;
-        ov.x = diffuse_update<F2D_DIV_F64>(l, bv.y, av.x, cv.x, rv.x, k.s);
-        ov.y = diffuse_update<F2D_DIV_F64>(bv.x, bv.z, av.y, cv.y, rv.y, k.s);
-        ov.z = diffuse_update<F2D_DIV_F64>(bv.y, bv.w, av.z, cv.z, rv.z, k.s);
-        ov.w = diffuse_update<F2D_DIV_F64>(bv.z, rt, av.w, cv.w, rv.w, k.s);
-        return perm(ov);
-    }
-    const f2 WL = pk(l, lo_of(b.B));   // west of (x, z) = (left lane's w, y)
-    const f2 ER = pk(hi_of(b.A), rt);  // east of (y, w) = (z, right lane's x)
+__device__ __forceinline__ float4 relax_row(const float4& a, const float4& b, const float4& c, float l, float rt,
+                                            const float4& rhs, const DiffuseCoef& k) {
+    float4 o;
     if (DIFFUSE) {
-        o.A = diffuse2(WL, b.B, a.A, c.A, rhs.A, k);
-        o.B = diffuse2(b.A, ER, a.B, c.B, rhs.B, k);
+        o.x = diffuse_update<DIVMODE>(l, b.y, a.x, c.x, rhs.x, k);
+        o.y = diffuse_update<DIVMODE>(b.x, b.z, a.y, c.y, rhs.y, k);
+        o.z = diffuse_update<DIVMODE>(b.y, b.w, a.z, c.z, rhs.z, k);
+        o.w = diffuse_update<DIVMODE>(b.z, rt, a.w, c.w, rhs.w, k);
     } else {
-        o.A = pressure2(rhs.A, b.B, WL, c.A, a.A, k.q);
-        o.B = pressure2(rhs.B, ER, b.A, c.B, a.B, k.q);
+        o.x = pressure_update(rhs.x, b.y, l, c.x, a.x);
+        o.y = pressure_update(rhs.y, b.z, b.x, c.y, a.y);
+        o.z = pressure_update(rhs.z, b.w, b.y, c.z, a.z);
+        o.w = pressure_update(rhs.w, rt, b.z, c.w, a.w);
     }
     return o;
 }
 
-// domain edge columns of an interior row: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32)
-__device__ __forceinline__ P fix_edge_cols(const P& v, bool has_left, bool has_right, bool neg) {
-    float4 f = unperm(v);
-    f.x = has_left ? apply_sign(f.y, neg) : f.x;
-    f.w = has_right ? apply_sign(f.z, neg) : f.w;
-    return perm(f);
-}
-
 // edge row from the adjacent interior row of the same level; corner cells keep `keep`
-__device__ __forceinline__ P edge_row(const P& inner_p, const P& keep_p, bool neg, bool has_left, bool has_right) {
-    const float4 inner = unperm(inner_p), keep = unperm(keep_p);
+__device__ __forceinline__ float4 edge_row(const float4& inner, const float4& keep, bool neg, bool has_left,
+                                           bool has_right) {
     float4 o;
     o.x = apply_sign(inner.x, neg);
     o.y = apply_sign(inner.y, neg);
@@ -247,24 +139,43 @@ __device__ __forceinline__ P edge_row(const P& inner_p, const P& keep_p, bool ne
     o.w = apply_sign(inner.w, neg);
     if (has_left) o.x = keep.x;
     if (has_right) o.w = keep.w;
-    return perm(o);
+    return o;
 }
+
+// ---- shared-memory rings (32-bit shared addresses, lane offset included in the base)
+// landing rings (kRingP slots of one row each, the block aligned to its own size): slot of row `row`
+__device__ __forceinline__ unsigned slot8(unsigned base, int row) { return (((unsigned)row << 9) & ((kRingP - 1) << 9)) | base; }
+// Mirrored rhs ring (rhs in shared memory): row i lives in slot i & 15; rows with (i & 8) == 0 are ALSO written to
+// slot 16 + (i & 15).  The rows r-1 .. r-T (T <= 8) a step reads are then contiguous below one read pointer:
+//   (r & 8) != 0: slots (r & 15) - 1 ... >= 0, the plain ring;
+//   (r & 8) == 0: from 16 + (r & 15) downwards -- mirrors first, then the plain slots 15, 14, ...
+// so level s reads its row at the compile-time offset -(s + 1) * 512 from slot_rd(base, r).
+__device__ __forceinline__ unsigned slot_wr(unsigned base, int row) { return base + (((unsigned)row << 9) & ((kRingR - 1) << 9)); }
+__device__ __forceinline__ bool mirrored(int row) { return (row & kMirror) == 0; }
+__device__ __forceinline__ unsigned slot_rd(unsigned base, int r) { return slot_wr(base, r) + (mirrored(r) ? (unsigned)(kRingR << 9) : 0u); }
+static_assert(kMirror == 8 && kRingR == 16, "the mirror rule is bit 3 of the row index");
 
 // per-warp constants of one (strip, chunk)
 struct Ctx {
     const float* prev;  // lane-adjusted: + column of this lane
     const float* rhs;
     float* next;
-    unsigned sp, sr;  // the two async-copy rings as 32-bit shared addresses (lane offset included), each
-                      // aligned to its own size so that a slot is ((row << 9) & mask) | base
-    unsigned sd;      // fused divergence: ring of computed divergence rows (the relaxation's rhs)
-    float* aux;       // fused divergence: the divergence field written for the later passes
+    unsigned sp, sr;  // the two async-copy rings (sp: iterate, always a landing ring; sr: rhs -- a landing ring, or the
+                      // mirrored ring when the relaxation reads its rhs from shared memory)
+    unsigned sd;      // fused first passes, rhs in shared memory: mirrored ring of the COMPUTED rhs rows
+    float* aux;       // fused divergence: the divergence field written for the later passes; fused add_sources: x0
     float mhalf_h;    // fused divergence: -0.5f * h; fused add_sources: dt
     int row_top, row_bot;  // local index of the global top / bottom edge row (or out of range)
-    Coef2 coef;
+    DiffuseCoef coef;
     int pitch, rs, re, y0, y1;
     int cp_bytes;
     bool top_dom, bot_dom, own_x, has_left, has_right, edge_warp, neg_c, neg_r;
+};
+
+// running element offsets of the rows a step touches (advanced by one pitch per step: no per-row multiplication)
+struct Run {
+    int off_in;   // row r + PFD (the row whose async copy is issued)
+    int off_out;  // row r - T   (the row the last level stores)
 };
 
 // RS consecutive row steps starting at relative row rb (a multiple of RS, so rb % 3 == 0 and the
@@ -275,9 +186,11 @@ struct Ctx {
 // feed cells outside the dependency cone of the rows this warp stores, and the store itself is
 // predicated on the owned row range.  Only blocks in which a level meets a GLOBAL top or bottom edge
 // row (edge rule, corner carry) take the checked path (FAST == false).
-template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool FAST, bool EDGE, int RS, int RINGR, int NRH>
-__device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, P (&W)[T][3], P (&RH)[NRH],
-                                          P& out_prev, float (&wl)[T], float (&er)[T], float4 (&UV)[2][3]) {
+// EDGE: this warp's strip holds a domain edge column; interior strips are compiled without the edge-column fix.
+template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool FAST, bool EDGE, int RS, int NRH>
+__device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int nsteps, float4 (&W)[T][3], float4 (&RH)[NRH],
+                                          float4& out_prev, float (&wl)[T], float (&er)[T], float4 (&UV)[2][3]) {
+    static_assert(T <= kMirror, "the mirrored ring covers T <= 8 rows");
     // PIN_ZERO == 2: the first pressure pass with the divergence fused in (gpu.cu:164-177 + :376): the two
     // async rings carry u and v rows instead of iterate and rhs; the rhs row r-1 is computed on the fly
     constexpr bool FUSE = (PIN_ZERO == 2);
@@ -285,7 +198,8 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, P (
     // rings carry the field and its source; x0 = FMA(dt, s, f) is formed per row, used as iterate AND rhs,
     // and written out as the rhs of the later passes
     constexpr bool FSRC = (PIN_ZERO == 3);
-    constexpr unsigned MASKR = (FUSE || FSRC) ? ((kRingP - 1) << 9) : ((RINGR - 1) << 9);  // landing zone only
+    constexpr bool RHS_LANDS_MIRRORED = !RHS_REGS && !FUSE && !FSRC;  // the async copy itself fills the mirrored ring
+    const bool hl = EDGE && cx.has_left, hr = EDGE && cx.has_right;
 #pragma unroll
     for (int k = 0; k < RS; ++k) {
         const int rr = rb + k;
@@ -296,9 +210,16 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, P (
         {
             const int rl = r + kPFD;
             if (rl <= cx.re) {
-                const size_t off = (size_t)rl * cx.pitch;
-                if (PIN_ZERO != 1) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
-                cp_async16_s((((unsigned)rl << 9) & MASKR) | cx.sr, cx.rhs + off, cx.cp_bytes);
+                if (PIN_ZERO != 1) cp_async16_s(slot8(cx.sp, rl), cx.prev + st.off_in, cx.cp_bytes);
+                if (RHS_LANDS_MIRRORED) {
+                    // two copies, branch-free: the slot and its mirror (a row without a mirror is simply written to its
+                    // slot twice; a branch here would split the row step into several basic blocks)
+                    const unsigned w = slot_wr(cx.sr, rl);
+                    cp_async16_s(w, cx.rhs + st.off_in, cx.cp_bytes);
+                    cp_async16_s(w + (mirrored(rl) ? (unsigned)(kRingR << 9) : 0u), cx.rhs + st.off_in, cx.cp_bytes);
+                } else {
+                    cp_async16_s(slot8(cx.sr, rl), cx.rhs + st.off_in, cx.cp_bytes);
+                }
             }
             cp_async_commit();
         }
@@ -306,36 +227,33 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, P (
         cp_async_wait<kPFD>();
         if (FAST || r <= cx.re) {  // FAST: past the last input row this re-reads a stale ring slot (harmless)
             if (FSRC) {
-                const float4 f4 = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);
-                const float4 s4 = lds128((((unsigned)r << 9) & MASKR) | cx.sr);
+                const float4 f4 = lds128(slot8(cx.sp, r));
+                const float4 s4 = lds128(slot8(cx.sr, r));
                 const bool row_in = (r != cx.row_top) && (r != cx.row_bot);  // global interior row
                 float4 x0;
-                x0.x = (row_in && !cx.has_left) ? __fmaf_rn(cx.mhalf_h, s4.x, f4.x) : f4.x;  // mhalf_h carries dt here
+                x0.x = (row_in && !hl) ? __fmaf_rn(cx.mhalf_h, s4.x, f4.x) : f4.x;  // mhalf_h carries dt here
                 x0.y = row_in ? __fmaf_rn(cx.mhalf_h, s4.y, f4.y) : f4.y;
                 x0.z = row_in ? __fmaf_rn(cx.mhalf_h, s4.z, f4.z) : f4.z;
-                x0.w = (row_in && !cx.has_right) ? __fmaf_rn(cx.mhalf_h, s4.w, f4.w) : f4.w;
-                const P x0p = perm(x0);
-                W[0][m3(k)] = x0p;
-                if (RHS_REGS)
-                    RH[mrs(k, RS)] = x0p;
-                else
-                    sts_p((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sd, x0p);
-                if (cx.own_x && r >= cx.y0 && r < cx.y1 && r <= cx.re) st_global_f4(cx.aux + (size_t)r * cx.pitch, x0);
+                x0.w = (row_in && !hr) ? __fmaf_rn(cx.mhalf_h, s4.w, f4.w) : f4.w;
+                W[0][m3(k)] = x0;
+                if (RHS_REGS) {
+                    RH[mrs(k, RS)] = x0;
+                } else {
+                    const unsigned w = slot_wr(cx.sd, r);
+                    sts128(w, x0);
+                    if (mirrored(r)) sts128(w + (kRingR << 9), x0);
+                }
+                if (cx.own_x && r >= cx.y0 && r < cx.y1 && r <= cx.re) st_global_f4(cx.aux + (st.off_out + T * cx.pitch), x0);
             } else if (!PIN_ZERO)
-                W[0][m3(k)] = perm(lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp));
+                W[0][m3(k)] = lds128(slot8(cx.sp, r));
             else
-                W[0][m3(k)] = zero_p();
+                W[0][m3(k)] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (FSRC) {
             } else if (FUSE) {
-                UV[0][m3(k)] = lds128((((unsigned)r << 9) & ((kRingP - 1) << 9)) | cx.sp);  // u row r
-                UV[1][m3(k)] = lds128((((unsigned)r << 9) & MASKR) | cx.sr);                // v row r
+                UV[0][m3(k)] = lds128(slot8(cx.sp, r));  // u row r
+                UV[1][m3(k)] = lds128(slot8(cx.sr, r));  // v row r
             } else if (RHS_REGS) {
-                RH[mrs(k, RS)] = perm(lds128((((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sr));
-            } else {
-                // the rhs row just landed in (x, y, z, w) order: re-write it as (x, z, y, w) so that each of its T
-                // later reads is one 16-byte load into two aligned pairs (every lane touches only its own 16 bytes)
-                const unsigned slot = (((unsigned)r << 9) & ((RINGR - 1) << 9)) | cx.sr;
-                sts_p(slot, perm(lds128(slot)));
+                RH[mrs(k, RS)] = lds128(slot8(cx.sr, r));
             }
         }
         if (FUSE) {
@@ -349,19 +267,22 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, P (
             dv.z = divergence_update(uc.w, uc.y, vs.z, vn.z, cx.mhalf_h);
             dv.w = divergence_update(ur, uc.z, vs.w, vn.w, cx.mhalf_h);
             // set_boundary_continuous on the divergence (gpu.cu:376): edge columns copy their neighbour
-            dv.x = cx.has_left ? dv.y : dv.x;
-            dv.w = cx.has_right ? dv.z : dv.w;
+            dv.x = hl ? dv.y : dv.x;
+            dv.w = hr ? dv.z : dv.w;
             const int qd = r - 1;
-            if (RHS_REGS)
-                RH[mrs(k - 1, RS)] = perm(dv);
-            else
-                sts_p((((unsigned)qd << 9) & ((RINGR - 1) << 9)) | cx.sd, perm(dv));
+            if (RHS_REGS) {
+                RH[mrs(k - 1, RS)] = dv;
+            } else {
+                const unsigned w = slot_wr(cx.sd, qd);
+                sts128(w, dv);
+                if (mirrored(qd)) sts128(w + (kRingR << 9), dv);
+            }
             if (cx.own_x && qd >= cx.rs + 1 && qd <= cx.re - 1) {
-                if (qd >= cx.y0 && qd < cx.y1) st_global_f4(cx.aux + (size_t)qd * cx.pitch, dv);
+                if (qd >= cx.y0 && qd < cx.y1) st_global_f4(cx.aux + (st.off_out + (T - 1) * cx.pitch), dv);
                 // the edge rows of the stored field copy the adjacent interior row, corners are the memset zeros
                 float4 e = dv;
-                e.x = cx.has_left ? 0.f : e.x;
-                e.w = cx.has_right ? 0.f : e.w;
+                e.x = hl ? 0.f : e.x;
+                e.w = hr ? 0.f : e.w;
                 if (qd == 1 && cx.top_dom && cx.y0 == 0) st_global_f4(cx.aux, e);
                 if (qd == cx.re - 1 && cx.bot_dom) st_global_f4(cx.aux + (size_t)cx.re * cx.pitch, e);
             }
@@ -370,9 +291,9 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, P (
         // west/east neighbours of the centre rows of all levels (rows produced in the previous step)
 #pragma unroll
         for (int s = 0; s < T; ++s) {
-            const P bb = W[s][m3(k - s - 1)];
-            wl[s] = __shfl_up_sync(0xffffffffu, hi_of(bb.B), 1);    // the left lane's w
-            er[s] = __shfl_down_sync(0xffffffffu, lo_of(bb.A), 1);  // the right lane's x
+            const float4 bb = W[s][m3(k - s - 1)];
+            wl[s] = __shfl_up_sync(0xffffffffu, bb.w, 1);
+            er[s] = __shfl_down_sync(0xffffffffu, bb.x, 1);
         }
 #endif
 
@@ -382,43 +303,48 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, P (
         const int s_lo = r - cx.re, s_hi = r - cx.rs - 2;
         const int s_top = cx.top_dom ? r - 2 : -1;           // level whose q == 1 (global top edge above it)
         const int s_bot = cx.bot_dom ? r - cx.re - 1 : -1;   // level whose q == re == global bottom edge row
+        // rhs in shared memory: the rows r-1 .. r-T sit contiguously below this pointer (mirrored ring)
+        const unsigned rd = RHS_REGS ? 0u : slot_rd((FUSE || FSRC) ? cx.sd : cx.sr, r);
 #pragma unroll
         for (int s = 0; s < T; ++s) {
             const int q = r - s - 1;
             const int sa = m3(k - s - 2), sm = m3(k - s - 1), sc = m3(k - s);
             const int sn = (s + 1 < T) ? s + 1 : 0;  // keeps the dead branch's index in range
             if (FAST || (s >= s_lo && s <= s_hi)) {
-                const P a = W[s][sa], b = W[s][sm], c = W[s][sc];
+                const float4 a = W[s][sa], b = W[s][sm], c = W[s][sc];
                 const float l = wl[s], rt = er[s];
-                P rhs;
+                float4 rhs;
                 if (RHS_REGS)
                     rhs = RH[mrs(k - s - 1, RS)];
                 else
-                    rhs = lds_p((((unsigned)q << 9) & ((RINGR - 1) << 9)) | ((FUSE || FSRC) ? cx.sd : cx.sr));
-                P nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
-                // only the strips that hold a domain edge column run this variant; branch-free selects, so a whole
-                // row step stays one basic block
-                if (EDGE) nw = fix_edge_cols(nw, cx.has_left, cx.has_right, cx.neg_c);
+                    rhs = lds128(rd - (unsigned)((s + 1) << 9));
+                float4 nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
+                // interior rows of an edge strip: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32), as
+                // two predicated selects (no branch) so that a whole row step stays one basic block
+                if (EDGE) {
+                    nw.x = cx.has_left ? apply_sign(nw.y, cx.neg_c) : nw.x;
+                    nw.w = cx.has_right ? apply_sign(nw.z, cx.neg_c) : nw.w;
+                }
                 if (s + 1 < T) {
                     W[sn][sm] = nw;
                 } else {
                     out_prev = nw;
-                    if (cx.own_x && q >= cx.y0 && q < cx.y1) st_global_f4(cx.next + (size_t)q * cx.pitch, unperm(nw));
+                    if (cx.own_x && q >= cx.y0 && q < cx.y1) st_global_f4(cx.next + st.off_out, nw);
                 }
                 if (!FAST && s == s_top) {  // global top edge row of the same level (corners kept)
-                    const P e = edge_row(nw, a, cx.neg_r, cx.has_left, cx.has_right);
+                    const float4 e = edge_row(nw, a, cx.neg_r, hl, hr);
                     if (s + 1 < T)
                         W[sn][sa] = e;
                     else if (cx.own_x && cx.y0 == 0)
-                        st_global_f4(cx.next, unperm(e));
+                        st_global_f4(cx.next, e);
                 }
             } else if (!FAST && s == s_bot && q >= cx.rs + 1) {  // global bottom edge row
-                const P inner = (s + 1 < T) ? W[sn][sa] : out_prev;
-                const P e = edge_row(inner, W[s][sm], cx.neg_r, cx.has_left, cx.has_right);
+                const float4 inner = (s + 1 < T) ? W[sn][sa] : out_prev;
+                const float4 e = edge_row(inner, W[s][sm], cx.neg_r, hl, hr);
                 if (s + 1 < T)
                     W[sn][sm] = e;
                 else if (cx.own_x && q >= cx.y0 && q < cx.y1)
-                    st_global_f4(cx.next + (size_t)q * cx.pitch, unperm(e));
+                    st_global_f4(cx.next + st.off_out, e);
             }
         }
         // 4. the centre row of level s in the NEXT step is row r - s (slot m3(k - s)); it is final now,
@@ -426,11 +352,28 @@ __device__ __forceinline__ void run_block(const Ctx& cx, int rb, int nsteps, P (
 #if F2D_SHFL_AHEAD
 #pragma unroll
         for (int s = 0; s < T; ++s) {
-            const P b = W[s][m3(k - s)];
-            wl[s] = __shfl_up_sync(0xffffffffu, hi_of(b.B), 1);
-            er[s] = __shfl_down_sync(0xffffffffu, lo_of(b.A), 1);
+            const float4 b = W[s][m3(k - s)];
+            wl[s] = __shfl_up_sync(0xffffffffu, b.w, 1);
+            er[s] = __shfl_down_sync(0xffffffffu, b.x, 1);
         }
 #endif
+        st.off_in += cx.pitch;
+        st.off_out += cx.pitch;
+    }
+}
+
+// all row steps of one warp; EDGE is the warp's class (chosen once, outside the row loop)
+template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool EDGE, int RS, int NRH>
+__device__ __forceinline__ void march(const Ctx& cx, Run& st, int nsteps, int top_lo, int top_hi, int bot_lo, int bot_hi,
+                                      float4 (&W)[T][3], float4 (&RH)[NRH], float4& out_prev, float (&wl)[T], float (&er)[T],
+                                      float4 (&UV)[2][3]) {
+    for (int rb = 0; rb < nsteps; rb += RS) {
+        const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
+        const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
+        if (!edge_block)
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, out_prev, wl, er, UV);
+        else
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, out_prev, wl, er, UV);
     }
 }
 
@@ -439,7 +382,6 @@ template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, int MIN
 __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch batch, StreamPlan plan) {
     constexpr int HALO = halo_of(T);
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;  // unroll factor of the row loop
-    constexpr int RINGR = ring_r_of(T, RHS_REGS);
     constexpr int NRH = RHS_REGS ? RS : 1;
     extern __shared__ float4 smem[];
 
@@ -465,7 +407,7 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
 
     const RelaxField& fld = batch.f[blockIdx.y];
     Ctx cx;
-    cx.coef = make_coef2(fld.coef);
+    cx.coef = fld.coef;
     cx.neg_c = (fld.kind == F2D_BND_OPPOSITE_HORIZONTAL);
     cx.neg_r = (fld.kind == F2D_BND_OPPOSITE_VERTICAL);
     cx.pitch = g.pitch;
@@ -487,10 +429,10 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     cx.rhs = fld.rhs + jsafe;
     cx.next = fld.next + jsafe;
     {
-        // [ring_r of warp 0 .. wpc-1][ring_p of warp 0 .. wpc-1], the block aligned to the rhs ring size so
-        // that "(row << 9) & mask | base" addresses a slot with two integer instructions
-        constexpr unsigned RB = RINGR * kLanes * 16u, PB = kRingP * kLanes * 16u;
-        const unsigned s0 = ((unsigned)__cvta_generic_to_shared(smem) + RB - 1u) & ~(RB - 1u);
+        // [rhs rings of warp 0 .. wpc-1][landing rings ...]: a landing ring is 4 KB and 4 KB-aligned ("(row << 9) & mask
+        // | base" addresses a slot with two integer instructions); the mirrored rhs ring is 12 KB per warp
+        constexpr unsigned RB = ring_r_slots(RHS_REGS) * kLanes * 16u, PB = kRingP * kLanes * 16u;
+        const unsigned s0 = ((unsigned)__cvta_generic_to_shared(smem) + PB - 1u) & ~(PB - 1u);
         if (PIN_ZERO >= 2) {
             // fused divergence / add_sources: [computed rhs ring (RB) x wpc][landing ring (PB) x wpc][landing ring (PB) x wpc]
             cx.sd = s0 + (unsigned)warp_in_cta * RB + (unsigned)lane * 16u;
@@ -524,9 +466,9 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     const int top_lo = cx.top_dom ? 2 : 1 << 30, top_hi = cx.top_dom ? T + 1 : -1;
     const int bot_lo = cx.bot_dom ? cx.re + 1 : 1 << 30, bot_hi = cx.bot_dom ? cx.re + T : -1;
 
-    P W[T][3];
-    P RH[NRH];
-    P out_prev = zero_p();
+    float4 W[T][3];
+    float4 RH[NRH];
+    float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
     float wl[T], er[T];
     float4 UV[2][3];
 #pragma unroll
@@ -535,43 +477,37 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     for (int s = 0; s < T; ++s) {
         wl[s] = er[s] = 0.f;
 #pragma unroll
-        for (int m = 0; m < 3; ++m) W[s][m] = zero_p();
+        for (int m = 0; m < 3; ++m) W[s][m] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int m = 0; m < NRH; ++m) RH[m] = zero_p();
+    for (int m = 0; m < NRH; ++m) RH[m] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     // ---- prologue: rows rs .. rs+PFD-1 in flight
+    constexpr bool RHS_LANDS_MIRRORED = !RHS_REGS && PIN_ZERO < 2;
 #pragma unroll
     for (int p = 0; p < kPFD; ++p) {
         const int rl = cx.rs + p;
         if (rl <= cx.re) {
             const size_t off = (size_t)rl * cx.pitch;
-            if (PIN_ZERO != 1) cp_async16_s((((unsigned)rl << 9) & ((kRingP - 1) << 9)) | cx.sp, cx.prev + off, cx.cp_bytes);
-            cp_async16_s((((unsigned)rl << 9) & ((PIN_ZERO >= 2 ? kRingP - 1 : RINGR - 1) << 9)) | cx.sr, cx.rhs + off, cx.cp_bytes);
+            if (PIN_ZERO != 1) cp_async16_s(slot8(cx.sp, rl), cx.prev + off, cx.cp_bytes);
+            if (RHS_LANDS_MIRRORED) {
+                const unsigned w = slot_wr(cx.sr, rl);
+                cp_async16_s(w, cx.rhs + off, cx.cp_bytes);
+                if (mirrored(rl)) cp_async16_s(w + (kRingR << 9), cx.rhs + off, cx.cp_bytes);
+            } else {
+                cp_async16_s(slot8(cx.sr, rl), cx.rhs + off, cx.cp_bytes);
+            }
         }
         cp_async_commit();
     }
+    Run st;
+    st.off_in = (cx.rs + kPFD) * cx.pitch;
+    st.off_out = (cx.rs - T) * cx.pitch;
 
-    // the edge-column variant is chosen once per warp (warp-uniform), outside the row loop
-    if (!cx.edge_warp) {
-        for (int rb = 0; rb < nsteps; rb += RS) {
-            const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
-            const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
-            if (!edge_block)
-                run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
-            else
-                run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, false, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
-        }
-    } else {
-        for (int rb = 0; rb < nsteps; rb += RS) {
-            const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
-            const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
-            if (!edge_block)
-                run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
-            else
-                run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, true, RS, RINGR, NRH>(cx, rb, nsteps, W, RH, out_prev, wl, er, UV);
-        }
-    }
+    if (!cx.edge_warp)
+        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV);
+    else
+        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV);
     cp_async_wait<0>();
 }
 
@@ -613,8 +549,9 @@ cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& t
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;
     int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
     wpc = std::min(wpc, 4);  // __launch_bounds__(128, ...)
-    const size_t smem = (size_t)wpc * (kRingP + ring_r_of(T, RHS_REGS) + (PIN_ZERO >= 2 ? kRingP : 0)) * kLanes * sizeof(float4) +
-                        (size_t)ring_r_of(T, RHS_REGS) * kLanes * sizeof(float4);  // alignment slack
+    // rhs ring(s) + iterate landing ring(s) per warp (see the kernel's layout comment) + 4 KB of alignment slack
+    const size_t smem = (size_t)wpc * (ring_r_slots(RHS_REGS) + kRingP + (PIN_ZERO >= 2 ? kRingP : 0)) * kLanes * sizeof(float4) +
+                        (size_t)kRingP * kLanes * sizeof(float4);
     // per device (function attributes live in the device's context) and per CTA size; a failed opt-in to more than
     // 48 KB of dynamic shared memory or a failed occupancy query is reported here, not at some later launch
     static int occ_cache_dev[16][9] = {};
