@@ -35,8 +35,9 @@ void launch_jacobi_naive(const Geom& g, const RelaxBatch& b, bool diffuse, int d
 void launch_divergence(const Geom& g, const float* u, const float* v, float* div, float h, cudaStream_t st);
 void launch_gradient(const Geom& g, const float* p, const float* u_in, const float* v_in, float* u_out,
                      float* v_out, float h, cudaStream_t st);
+// rows [valid_lo, valid_hi) of u0 / v0 are valid; *oob_flag is raised when an owned cell's back-trace leaves them
 void launch_advect_velocity(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out,
-                            float dt0, int own_begin, int own_end, int* oob_flag, cudaStream_t st);
+                            float dt0, int own_begin, int own_end, int valid_lo, int valid_hi, int* oob_flag, cudaStream_t st);
 void launch_add_rows(const Geom& g, float* f, int row0, int nrows, const float* src, cudaStream_t st);
 // forward scatter of `src` by (u,v) into `out` (must be zeroed); rows [own_begin, own_end) are the
 // source rows this slab owns.  *oob_flag (device int) is set if a target row left the local slab.

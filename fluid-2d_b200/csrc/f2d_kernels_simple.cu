@@ -269,7 +269,8 @@ void launch_gradient(const Geom& g, const float* p, const float* u_in, const flo
 __global__ void __launch_bounds__(kBx* kBy) k_advect_velocity(Geom g, const float* __restrict__ u0,
                                                              const float* __restrict__ v0,
                                                              float* __restrict__ u_out, float* __restrict__ v_out,
-                                                             float dt0, int own_begin, int own_end, int* oob_flag) {
+                                                             float dt0, int own_begin, int own_end, int valid_lo, int valid_hi,
+                                                             int* oob_flag) {
     F2D_CELL_IJ();
     const CellSrc cu = classify_cell(g, i, j, F2D_BND_OPPOSITE_HORIZONTAL);
     const CellSrc cv = classify_cell(g, i, j, F2D_BND_OPPOSITE_VERTICAL);
@@ -285,9 +286,11 @@ __global__ void __launch_bounds__(kBx* kBy) k_advect_velocity(Geom g, const floa
     x = fmaxf(1.5f, fminf((float)g.cols - 1.5f, x));
     y = fmaxf(1.5f, fminf((float)g.grows - 1.5f, y));
     const Bilinear b = bilinear_setup(x, y);
-    // local row of the gather; a slab's halo is sized from the CFL bound, clamp defensively
+    // local rows li0, li0 + 1 of the gather.  [valid_lo, valid_hi) are the rows of u0 / v0 known to be valid (the halo
+    // rows refreshed by the last exchange minus what later stencils invalidated): an owned cell whose back-trace leaves
+    // them broke the displacement bound the exchange schedule was built for -> error flag, never a silent stale read
     int li0 = b.i0 - g.grow0;
-    if ((li0 < 0 || li0 > g.rows - 2) && i >= own_begin && i < own_end) *oob_flag = 1;  // CFL promise broken
+    if ((li0 < valid_lo || li0 + 1 >= valid_hi) && i >= own_begin && i < own_end) *oob_flag = 1;
     li0 = max(0, min(g.rows - 2, li0));
     const size_t a = (size_t)li0 * g.pitch + b.j0;
     const float un = bilinear_gather(b, __ldg(u0 + a), __ldg(u0 + a + 1), __ldg(u0 + a + g.pitch), __ldg(u0 + a + g.pitch + 1));
@@ -297,8 +300,8 @@ __global__ void __launch_bounds__(kBx* kBy) k_advect_velocity(Geom g, const floa
 }
 
 void launch_advect_velocity(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out,
-                            float dt0, int own_begin, int own_end, int* oob_flag, cudaStream_t st) {
-    k_advect_velocity<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u0, v0, u_out, v_out, dt0, own_begin, own_end, oob_flag);
+                            float dt0, int own_begin, int own_end, int valid_lo, int valid_hi, int* oob_flag, cudaStream_t st) {
+    k_advect_velocity<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u0, v0, u_out, v_out, dt0, own_begin, own_end, valid_lo, valid_hi, oob_flag);
 }
 
 // rows [row0, row0 + nrows) of f += src (src is a dense nrows x pitch block): the receiving end of the

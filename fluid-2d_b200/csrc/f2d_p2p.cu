@@ -69,10 +69,21 @@ __global__ void __launch_bounds__(256) k_halo_xchg(XchgParams P) {
     __syncthreads();
     const unsigned e = e_s;
     const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    // the push: local loads, 16-byte peer stores over NVLink.  Four independent loads are in flight per thread before
+    // the first store (the copy is latency-, not bandwidth-bound: a few MB per exchange)
     for (int s = 0; s < P.nseg; ++s) {
         const float4* __restrict__ src = P.seg[s].src;
         float4* dst = P.seg[s].dst;
-        for (unsigned i = tid; i < P.seg[s].n4; i += nth) dst[i] = src[i];
+        const unsigned n4 = P.seg[s].n4;
+        unsigned i = tid;
+        for (; i + 3u * nth < n4; i += 4u * nth) {
+            const float4 a = __ldg(src + i), b = __ldg(src + i + nth), c = __ldg(src + i + 2u * nth), d = __ldg(src + i + 3u * nth);
+            dst[i] = a;
+            dst[i + nth] = b;
+            dst[i + 2u * nth] = c;
+            dst[i + 3u * nth] = d;
+        }
+        for (; i < n4; i += nth) dst[i] = __ldg(src + i);
     }
     __threadfence_system();
     __syncthreads();
@@ -91,6 +102,6 @@ __global__ void __launch_bounds__(256) k_halo_xchg(XchgParams P) {
     }
 }
 
-void launch_halo_xchg(const XchgParams& p, cudaStream_t st) { k_halo_xchg<<<64, 256, 0, st>>>(p); }
+void launch_halo_xchg(const XchgParams& p, cudaStream_t st) { k_halo_xchg<<<128, 256, 0, st>>>(p); }
 
 }  // namespace f2d

@@ -23,6 +23,8 @@
 
 #include <dlfcn.h>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges cost nothing unless a profiler is attached
+
 #include "f2d_kernels.cuh"
 
 using namespace f2d;
@@ -56,6 +58,15 @@ int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
+
+// NVTX range per stage of the step driver (host-side enqueue / graph-capture time; replays of a captured graph show
+// up as one cudaGraphLaunch in a timeline, run with use_graph = 0 to see the stages on the device rows)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct GraphKey {
     float diffusion_rate, viscosity, dt;
@@ -109,7 +120,7 @@ struct f2d_solver {
     cudaEvent_t ev_in[3] = {nullptr, nullptr, nullptr}, ev_vel = nullptr, ev_fence = nullptr;
     cudaGraphExec_t host_exec[4] = {nullptr, nullptr, nullptr, nullptr};
     GraphKey host_key = {0.f, 0.f, 0.f, false};
-    uint64_t host_kernels[4] = {0, 0, 0, 0};
+    uint64_t host_kernels[4] = {0, 0, 0, 0}, host_xch[4] = {0, 0, 0, 0}, host_xbytes[4] = {0, 0, 0, 0};
     float *out_u = nullptr, *out_v = nullptr;
     float* hp_x0[2] = {nullptr, nullptr};         // add_sources outputs of u, v (alive from part 0/1 to part 2)
     const float* hp_res[2] = {nullptr, nullptr};  // diffused u, v
@@ -160,7 +171,18 @@ struct f2d_solver {
     // exchanged first.  One GPU: no neighbours, nothing to do.
     void* comm = nullptr;  // ncclComm_t
     int rank = 0, nranks = 1;
-    int cfl_cells = 8;     // bound on the advection displacement per step, in cells (caller's promise)
+    int cfl_cells = 8;     // bound on the advection displacement per step in rows: the caller's promise (default and
+                           // maximum: halo - 1), verified on the device by the advection kernels
+    void drop_graphs() {   // the exchange schedule is baked into the captured graphs
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+        graph_key.valid = false;
+        for (auto& e : host_exec) {
+            if (e) cudaGraphExecDestroy(e);
+            e = nullptr;
+        }
+        host_key.valid = false;
+    }
     float *rx_up = nullptr, *rx_down = nullptr;  // landing zones of the reverse (scatter) exchange
     char* arena = nullptr;                       // the single device allocation all of the above live in
     size_t arena_bytes = 0, field_stride = 0, rx_bytes = 0;
@@ -375,104 +397,150 @@ struct f2d_solver {
         return F2D_OK;
     }
 
+    // ---- the three chains of a step, shared by the device-resident step and by the pipelined solve() --------------
+    // add_sources + diffuse of n fields (gpu.cu:237-238, :243-246).  x0[i]: pool buffer that receives the field after
+    // add_sources (== the rhs of the relaxation); with `in_place_first` the first field is updated in place instead
+    // (density without the fused first pass).  res[i] = buffer holding the diffused field.
+    int diffuse_fields(int n, const int* flds, const int* kinds, const float* rates, float dt, float* const* x0, const float** res) {
+        const bool fuse_src = fuse_sources && cfg.jacobi_mode == F2D_JACOBI_STREAM && cfg.diffuse_iters > 0;
+        DiffuseCoef kc[kMaxBatch];
+        const float* x0c[kMaxBatch];
+        for (int i = 0; i < n; ++i) {
+            kc[i] = diffuse_coef(rates[i], dt);
+            x0c[i] = x0[i];
+        }
+        if (fuse_src) {
+            const float* in[kMaxBatch];
+            const float* srcs[kMaxBatch];
+            for (int i = 0; i < n; ++i) {
+                in[i] = state[flds[i]];
+                srcs[i] = state[flds[i] + 3];
+            }
+            return relax(n, in, x0c, kinds, kc, true, cfg.diffuse_iters, res, srcs, dt);
+        }
+        AddSourceBatch ab;
+        ab.n = n;
+        for (int i = 0; i < n; ++i) {
+            ab.f[i] = state[flds[i]];
+            ab.o[i] = x0[i];
+            ab.s[i] = state[flds[i] + 3];
+            set_inv(x0[i], get_inv(state[flds[i]]));  // pointwise: halo validity carries over
+        }
+        launch_add_sources(g, ab, dt, stream);
+        count();
+        return relax(n, x0c, x0c, kinds, kc, true, cfg.diffuse_iters, res);  // x0 == the field after add_sources
+    }
+
+    // density: forward scatter of `dd` (the diffused density) by the PRE-step (u, v), boundary pass + smooth into the
+    // density state (gpu.cu:239-240)
+    int density_advect(const float* dd, const float* u_pre, const float* v_pre, float dt) {
+        float* d = state[F2D_FIELD_DENSITY];
+        float* sc = acquire();
+        if (!sc) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        F2D_CUDA(cudaMemsetAsync(sc, 0, field_bytes, stream));  // gpu.cu:337
+        launch_scatter_density(g, dd, u_pre, v_pre, sc, dt0(dt), own_begin(), own_end(), oob_flag, stream);
+        count();
+        if (multi()) {
+            // splats that landed in halo rows belong to the neighbour slab: send them home and add,
+            // then refresh the halos for the radius-1 smooth
+            F2D_TRY(reverse_exchange_add(sc));
+            const float* one[1] = {sc};
+            F2D_TRY(exchange(one, 1));
+        }
+        launch_smooth_bnd(g, sc, d, cfg.smooth != 0, stream);  // gpu.cu:355 + :240
+        count();
+        set_inv(d, 1);
+        release(sc);
+        F2D_CUDA(cudaGetLastError());
+        return F2D_OK;
+    }
+
+    // velocity: project, self-advect, project (gpu.cu:247-252).  (u1, v1): the diffused velocity in pool buffers, which
+    // are overwritten by the advection; the result lands in (u_out, v_out).
+    int velocity_chain(const float* u1, const float* v1, float* u_out, float* v_out, float dt) {
+        float *u2 = acquire(), *v2 = acquire();
+        if (!u2 || !v2) return fail(F2D_ERR_STATE, "scratch pool exhausted");
+        F2D_TRY(project(u1, v1, u2, v2, cfg.project_iters));  // gpu.cu:247
+        // advect both components by (U0,V0) = (u2,v2) (gpu.cu:248-251); u1/v1 are free to be overwritten
+        float *u3 = const_cast<float*>(u1), *v3 = const_cast<float*>(v1);
+        {
+            // gather radius = displacement bound + bilinear footprint.  The bound is the caller's (cfl_cells, at most
+            // halo - 1) and is VERIFIED on the device: a back-trace that leaves the rows known to be valid raises the
+            // error flag f2d_sync reports, it never reads stale halo rows silently.
+            const int r = multi() ? cfl_cells + 1 : 0;
+            F2D_TRY(need({{u2, H() - r}, {v2, H() - r}}));
+            const int iuv = std::max(get_inv(u2), get_inv(v2));
+            const int valid_lo = has_up() ? iuv : 0, valid_hi = has_down() ? g.rows - iuv : g.rows;
+            launch_advect_velocity(g, u2, v2, u3, v3, dt0(dt), own_begin(), own_end(), valid_lo, valid_hi, oob_flag, stream);
+            count();
+            set_inv(u3, iuv + r);
+            set_inv(v3, iuv + r);
+        }
+        release(u2);
+        release(v2);
+        F2D_TRY(project(u3, v3, u_out, v_out, cfg.project_iters));  // gpu.cu:252
+        F2D_CUDA(cudaGetLastError());
+        return F2D_OK;
+    }
+
+    // halos of the state are assumed stale at the start of a step (only owned rows valid), so that the exchange
+    // schedule baked into a captured graph is right for every replay
+    int begin_step_bookkeeping() {
+        if (!multi()) return F2D_OK;
+        inv_table.clear();
+        set_inv(state[F2D_FIELD_DENSITY], H());
+        set_inv(state[F2D_FIELD_U], H());
+        set_inv(state[F2D_FIELD_V], H());
+        if (cfl_cells + 1 > H()) return fail(F2D_ERR_INVALID, "halo (%d) shallower than the advection radius (%d)", H(), cfl_cells + 1);
+        return F2D_OK;
+    }
+
+    int record_density_done() {
+        if (capturing)
+            F2D_CUDA(cudaEventRecordWithFlags(ev_density, stream, cudaEventRecordExternal));
+        else
+            F2D_CUDA(cudaEventRecord(ev_density, stream));
+        return F2D_OK;
+    }
+
     // One full solve() step on the device-resident state (order of gpu.cu:236-252).
     int enqueue_step(float diffusion_rate, float viscosity, float dt) {
         float *d = state[F2D_FIELD_DENSITY], *u = state[F2D_FIELD_U], *v = state[F2D_FIELD_V];
-        if (multi()) {
-            // assume nothing about the halos on entry (only owned rows valid), so that the exchange
-            // schedule baked into a captured graph is right for every replay
-            inv_table.clear();
-            set_inv(d, H());
-            set_inv(u, H());
-            set_inv(v, H());
-            if (cfl_cells + 1 > H()) return fail(F2D_ERR_INVALID, "halo (%d) shallower than the advection radius (%d)", H(), cfl_cells + 1);
-        }
-        // ---- add_sources + diffuse for d, u, v (gpu.cu:237-238, :243-246).  u and v get their sources OUT of
-        //      place: the density scatter below still needs the pre-step u, v (the reference runs the whole
-        //      density chain first, gpu.cu:236-240).  In stream mode add_sources is fused into the first
-        //      diffuse pass, which writes x0 (the field after add_sources == the rhs of the relaxation).
+        F2D_TRY(begin_step_bookkeeping());
+        NvtxRange step_range("f2d step");
+        // ---- add_sources + diffuse for d, u, v in one batch.  u and v get their sources OUT of place: the density
+        //      scatter below still needs the pre-step u, v (the reference runs the whole density chain first,
+        //      gpu.cu:236-240).  In stream mode add_sources is fused into the first diffuse pass, which writes x0.
         const bool fuse_src = fuse_sources && cfg.jacobi_mode == F2D_JACOBI_STREAM && cfg.diffuse_iters > 0;
         float *ds = fuse_src ? acquire() : d, *us = acquire(), *vs = acquire();
         if (!ds || !us || !vs) return fail(F2D_ERR_STATE, "scratch pool exhausted");
         const float* dif[3];
         {
+            NvtxRange r("add_sources + diffuse (d, u, v)");
+            const int flds[3] = {F2D_FIELD_DENSITY, F2D_FIELD_U, F2D_FIELD_V};
             const int kind[3] = {F2D_BND_CONTINUOUS, F2D_BND_OPPOSITE_HORIZONTAL, F2D_BND_OPPOSITE_VERTICAL};
-            const DiffuseCoef kc[3] = {diffuse_coef(diffusion_rate, dt), diffuse_coef(viscosity, dt), diffuse_coef(viscosity, dt)};
-            const float* x0[3] = {ds, us, vs};
-            if (fuse_src) {
-                const float* in[3] = {d, u, v};
-                const float* srcs[3] = {state[F2D_FIELD_DENSITY_SOURCE], state[F2D_FIELD_U_SOURCE], state[F2D_FIELD_V_SOURCE]};
-                F2D_TRY(relax(3, in, x0, kind, kc, true, cfg.diffuse_iters, dif, srcs, dt));
-            } else {
-                AddSourceBatch ab;
-                ab.n = 3;
-                ab.f[0] = d;
-                ab.o[0] = d;
-                ab.s[0] = state[F2D_FIELD_DENSITY_SOURCE];
-                ab.f[1] = u;
-                ab.o[1] = us;
-                ab.s[1] = state[F2D_FIELD_U_SOURCE];
-                ab.f[2] = v;
-                ab.o[2] = vs;
-                ab.s[2] = state[F2D_FIELD_V_SOURCE];
-                launch_add_sources(g, ab, dt, stream);
-                count();
-                set_inv(us, get_inv(u));  // pointwise: halo validity carries over
-                set_inv(vs, get_inv(v));
-                F2D_TRY(relax(3, x0, x0, kind, kc, true, cfg.diffuse_iters, dif));  // x0 == the field after add_sources
-            }
+            const float rates[3] = {diffusion_rate, viscosity, viscosity};
+            float* x0[3] = {ds, us, vs};
+            F2D_TRY(diffuse_fields(3, flds, kind, rates, dt, x0, dif));
         }
-        // ---- density: forward scatter by the PRE-step (u, v), boundary pass + smooth (gpu.cu:239-240)
         {
-            float* sc = acquire();
-            if (!sc) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-            F2D_CUDA(cudaMemsetAsync(sc, 0, field_bytes, stream));  // gpu.cu:337
-            launch_scatter_density(g, dif[0], u, v, sc, dt0(dt), own_begin(), own_end(), oob_flag, stream);
-            count();
+            NvtxRange r("density: scatter + smooth");
+            F2D_TRY(density_advect(dif[0], u, v, dt));
             if (dif[0] != d) release(dif[0]);
-            if (ds != d) release(ds);
-            if (multi()) {
-                // splats that landed in halo rows belong to the neighbour slab: send them home and add,
-                // then refresh the halos for the radius-1 smooth
-                F2D_TRY(reverse_exchange_add(sc));
-                const float* one[1] = {sc};
-                F2D_TRY(exchange(one, 1));
-            }
-            launch_smooth_bnd(g, sc, d, cfg.smooth != 0, stream);  // gpu.cu:355 + :240
-            count();
-            set_inv(d, 1);
-            release(sc);
+            if (ds != d && ds != dif[0]) release(ds);
             // density is final: let solve() start its download while the projections run
-            if (capturing)
-                F2D_CUDA(cudaEventRecordWithFlags(ev_density, stream, cudaEventRecordExternal));
-            else
-                F2D_CUDA(cudaEventRecord(ev_density, stream));
+            F2D_TRY(record_density_done());
         }
-        // ---- velocity: project, self-advect, project (gpu.cu:247-252)
         {
+            NvtxRange r("velocity: project, advect, project");
             const float *u1 = dif[1], *v1 = dif[2];
             if (u1 != us) {  // K > 0: the add_sources outputs are no longer needed
                 release(us);
                 release(vs);
             }
-            float *u2 = acquire(), *v2 = acquire();
-            if (!u2 || !v2) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-            F2D_TRY(project(u1, v1, u2, v2, cfg.project_iters));  // gpu.cu:247
-            // advect both components by (U0,V0) = (u2,v2) (gpu.cu:248-251); u1/v1 are free to be overwritten
-            float *u3 = const_cast<float*>(u1), *v3 = const_cast<float*>(v1);
-            {
-                const int r = cfl_cells + 1;  // gather radius: displacement bound + bilinear footprint
-                F2D_TRY(need({{u2, H() - r}, {v2, H() - r}}));
-                launch_advect_velocity(g, u2, v2, u3, v3, dt0(dt), own_begin(), own_end(), oob_flag, stream);
-                count();
-                set_inv(u3, std::max(get_inv(u2), get_inv(v2)) + r);
-                set_inv(v3, get_inv(u3));
-            }
-            release(u2);
-            release(v2);
-            F2D_TRY(project(u3, v3, u, v, cfg.project_iters));  // gpu.cu:252, result lands in the state buffers
-            release(u3);
-            release(v3);
+            F2D_TRY(velocity_chain(u1, v1, u, v, dt));  // result lands in the state buffers
+            release(u1);
+            release(v1);
         }
         F2D_CUDA(cudaGetLastError());
         return F2D_OK;
@@ -641,88 +709,48 @@ struct f2d_solver {
         return F2D_OK;
     }
 
-    // ================================================================ solve() pipeline parts (single GPU, F2D_SEM_GPU)
+    // ================================================================ solve() pipeline parts (F2D_SEM_GPU; one GPU or one slab)
     int enqueue_host_part(int part, float diffusion_rate, float viscosity, float dt) {
         float *d = state[F2D_FIELD_DENSITY], *u = state[F2D_FIELD_U], *v = state[F2D_FIELD_V];
         const bool fuse_src = fuse_sources && cfg.jacobi_mode == F2D_JACOBI_STREAM && cfg.diffuse_iters > 0;
+        if (part == 0) F2D_TRY(begin_step_bookkeeping());  // the four parts are always enqueued in order 0, 1, 2, 3
         if (part == 0 || part == 1) {  // gpu.cu:243-246 for one velocity component
-            const int fld = (part == 0) ? F2D_FIELD_U : F2D_FIELD_V;
+            NvtxRange r(part == 0 ? "solve part 0: add_sources + diffuse u" : "solve part 1: add_sources + diffuse v");
+            const int flds[1] = {part == 0 ? F2D_FIELD_U : F2D_FIELD_V};
             const int kind[1] = {part == 0 ? F2D_BND_OPPOSITE_HORIZONTAL : F2D_BND_OPPOSITE_VERTICAL};
-            const DiffuseCoef kc[1] = {diffuse_coef(viscosity, dt)};
-            float* x0 = acquire();
-            if (!x0) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-            const float* x0c[1] = {x0};
+            const float rates[1] = {viscosity};
+            float* x0[1] = {acquire()};
+            if (!x0[0]) return fail(F2D_ERR_STATE, "scratch pool exhausted");
             const float* res[1];
-            if (fuse_src) {
-                const float* in[1] = {state[fld]};
-                const float* srcs[1] = {state[fld + 3]};
-                F2D_TRY(relax(1, in, x0c, kind, kc, true, cfg.diffuse_iters, res, srcs, dt));
-            } else {
-                AddSourceBatch ab;
-                ab.n = 1;
-                ab.f[0] = state[fld];
-                ab.o[0] = x0;
-                ab.s[0] = state[fld + 3];
-                launch_add_sources(g, ab, dt, stream);
-                count();
-                F2D_TRY(relax(1, x0c, x0c, kind, kc, true, cfg.diffuse_iters, res));
-            }
-            hp_x0[part] = x0;
+            F2D_TRY(diffuse_fields(1, flds, kind, rates, dt, x0, res));
+            hp_x0[part] = x0[0];
             hp_res[part] = res[0];
             return F2D_OK;
         }
         if (part == 2) {  // gpu.cu:247-252
+            NvtxRange r("solve part 2: project, advect, project");
             const float *u1 = hp_res[0], *v1 = hp_res[1];
             if (u1 != hp_x0[0]) release(hp_x0[0]);
             if (v1 != hp_x0[1]) release(hp_x0[1]);
-            float *u2 = acquire(), *v2 = acquire();
-            if (!u2 || !v2) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-            F2D_TRY(project(u1, v1, u2, v2, cfg.project_iters));
-            float *u3 = const_cast<float*>(u1), *v3 = const_cast<float*>(v1);
-            launch_advect_velocity(g, u2, v2, u3, v3, dt0(dt), own_begin(), own_end(), oob_flag, stream);
-            count();
-            release(u2);
-            release(v2);
-            F2D_TRY(project(u3, v3, out_u, out_v, cfg.project_iters));
-            release(u3);
-            release(v3);
+            F2D_TRY(velocity_chain(u1, v1, out_u, out_v, dt));
+            release(u1);
+            release(v1);
             hp_x0[0] = hp_x0[1] = nullptr;
             hp_res[0] = hp_res[1] = nullptr;
-            F2D_CUDA(cudaGetLastError());
             return F2D_OK;
         }
         // part 3: add_sources + diffuse + scatter + smooth of the density (gpu.cu:237-240), by the PRE-step u, v
+        NvtxRange r("solve part 3: density chain");
+        const int flds[1] = {F2D_FIELD_DENSITY};
         const int kind[1] = {F2D_BND_CONTINUOUS};
-        const DiffuseCoef kc[1] = {diffuse_coef(diffusion_rate, dt)};
-        float* ds = fuse_src ? acquire() : d;
-        if (!ds) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-        const float* x0c[1] = {ds};
+        const float rates[1] = {diffusion_rate};
+        float* x0[1] = {fuse_src ? acquire() : d};
+        if (!x0[0]) return fail(F2D_ERR_STATE, "scratch pool exhausted");
         const float* dif[1];
-        if (fuse_src) {
-            const float* in[1] = {d};
-            const float* srcs[1] = {state[F2D_FIELD_DENSITY_SOURCE]};
-            F2D_TRY(relax(1, in, x0c, kind, kc, true, cfg.diffuse_iters, dif, srcs, dt));
-        } else {
-            AddSourceBatch ab;
-            ab.n = 1;
-            ab.f[0] = d;
-            ab.o[0] = d;
-            ab.s[0] = state[F2D_FIELD_DENSITY_SOURCE];
-            launch_add_sources(g, ab, dt, stream);
-            count();
-            F2D_TRY(relax(1, x0c, x0c, kind, kc, true, cfg.diffuse_iters, dif));
-        }
-        float* sc = acquire();
-        if (!sc) return fail(F2D_ERR_STATE, "scratch pool exhausted");
-        F2D_CUDA(cudaMemsetAsync(sc, 0, field_bytes, stream));
-        launch_scatter_density(g, dif[0], u, v, sc, dt0(dt), own_begin(), own_end(), oob_flag, stream);
-        count();
+        F2D_TRY(diffuse_fields(1, flds, kind, rates, dt, x0, dif));
+        F2D_TRY(density_advect(dif[0], u, v, dt));
         if (dif[0] != d) release(dif[0]);
-        if (ds != d) release(ds);
-        launch_smooth_bnd(g, sc, d, cfg.smooth != 0, stream);
-        count();
-        release(sc);
-        F2D_CUDA(cudaGetLastError());
+        if (x0[0] != d && x0[0] != dif[0]) release(x0[0]);
         return F2D_OK;
     }
 
@@ -739,15 +767,20 @@ struct f2d_solver {
         if (last_p) release(last_p);
         last_div = last_p = nullptr;
         for (int part = 0; part < 4; ++part) {
-            const uint64_t before = launches;
+            const uint64_t before = launches, xbefore = exchanges, bbefore = xbytes;
             cudaGraph_t graph = nullptr;
-            F2D_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            // relaxed mode: NCCL (multi-GPU) may issue its own runtime calls while we capture
+            F2D_CUDA(cudaStreamBeginCapture(stream, multi() ? cudaStreamCaptureModeRelaxed : cudaStreamCaptureModeThreadLocal));
             capturing = true;
             int rc = enqueue_host_part(part, diffusion_rate, viscosity, dt);
             capturing = false;
             cudaError_t ce = cudaStreamEndCapture(stream, &graph);
             host_kernels[part] = launches - before;
             launches = before;
+            host_xch[part] = exchanges - xbefore;
+            exchanges = xbefore;
+            host_xbytes[part] = xbytes - bbefore;
+            xbytes = bbefore;
             if (rc != F2D_OK) {
                 if (graph) cudaGraphDestroy(graph);
                 return rc;
@@ -765,6 +798,8 @@ struct f2d_solver {
         if (!cfg.use_graph) return enqueue_host_part(part, diffusion_rate, viscosity, dt);
         F2D_CUDA(cudaGraphLaunch(host_exec[part], stream));
         launches += host_kernels[part];
+        exchanges += host_xch[part];
+        xbytes += host_xbytes[part];
         return F2D_OK;
     }
 
@@ -1151,12 +1186,8 @@ F2D_API int f2d_p2p_connect(f2d_solver* s, int rank, int nranks, const unsigned 
     s->p2p = true;
     s->rank = rank;
     s->nranks = nranks;
-    s->cfl_cells = cfl_cells > 0 ? cfl_cells : 8;
-    if (s->graph_exec) {
-        cudaGraphExecDestroy(s->graph_exec);
-        s->graph_exec = nullptr;
-        s->graph_key.valid = false;
-    }
+    s->cfl_cells = cfl_cells > 0 ? std::min(cfl_cells, s->H() - 1) : s->H() - 1;
+    s->drop_graphs();
     return F2D_OK;
 }
 
@@ -1189,7 +1220,7 @@ F2D_API int f2d_comm_init(f2d_solver* s, const char* id128, int rank, int nranks
     s->comm = comm;
     s->rank = rank;
     s->nranks = nranks;
-    s->cfl_cells = cfl_cells > 0 ? cfl_cells : 8;
+    s->cfl_cells = cfl_cells > 0 ? std::min(cfl_cells, s->H() - 1) : s->H() - 1;
     {
         // establish the P2P connections eagerly (outside any graph capture) with one exchange of each kind
         float* t = s->acquire();
@@ -1204,11 +1235,7 @@ F2D_API int f2d_comm_init(f2d_solver* s, const char* id128, int rank, int nranks
         s->exchanges = 0;
         s->inv_table.clear();
     }
-    if (s->graph_exec) {  // a graph captured before had no exchanges in it
-        cudaGraphExecDestroy(s->graph_exec);
-        s->graph_exec = nullptr;
-        s->graph_key.valid = false;
-    }
+    s->drop_graphs();  // a graph captured before had no exchanges in it
     return F2D_OK;
 }
 
@@ -1561,7 +1588,8 @@ F2D_API int f2d_sync(f2d_solver* s) {
     }
     if (oob) {
         cudaMemset(s->oob_flag, 0, sizeof(int));
-        return fail(F2D_ERR_STATE, "density scatter left the slab: displacement exceeded the halo (CFL bound violated)");
+        return fail(F2D_ERR_STATE, "advection left the rows this slab holds valid: the displacement of a step exceeded cfl_cells "
+                                   "(at most halo - 1 rows); the state is invalid from that step on");
     }
     return F2D_OK;
 }
@@ -1573,7 +1601,7 @@ F2D_API int f2d_solve_host(f2d_solver* s, float* density, const float* density_s
     const size_t host_bytes = (size_t)s->g.rows * s->g.cols * sizeof(float);
     const void* hosts[6] = {density, u, v, density_source, u_source, v_source};
     for (const void* h : hosts) s->pin_host(h, host_bytes);
-    if (s->host_pipeline && !s->multi() && !s->cpu_sem() && s->field_bytes >= s->host_pipeline_min_bytes) {
+    if (s->host_pipeline && !s->cpu_sem() && s->field_bytes >= s->host_pipeline_min_bytes) {
         F2D_TRY(s->solve_host_pipelined(density, density_source, diffusion_rate, u, v, u_source, v_source, viscosity, dt));
         return f2d_sync(s);
     }
@@ -1694,7 +1722,7 @@ F2D_API int f2d_stage_advect_velocity(f2d_solver* s, float dt) {
     if (s->cpu_sem())
         launch_advect_velocity_nofma(s->g, u0, v0, u, v, s->dt0_cpu(dt), s->stream);  // cpp:26-29
     else
-        launch_advect_velocity(s->g, u0, v0, u, v, s->dt0(dt), s->own_begin(), s->own_end(), s->oob_flag, s->stream);
+        launch_advect_velocity(s->g, u0, v0, u, v, s->dt0(dt), s->own_begin(), s->own_end(), 0, s->g.rows, s->oob_flag, s->stream);
     s->count();
     s->release(u0);
     s->release(v0);

@@ -46,8 +46,9 @@ def partition(global_rows, world, halo, rank):
 
 
 def take(slab, a):
-    """Local slab (halo rows included) of a global host array."""
-    return np.ascontiguousarray(a[slab.row_offset:slab.row_offset + slab.rows])
+    """Local slab (halo rows included) of a global host array, as an independent COPY (a contiguous row range of a
+    C-ordered array would otherwise be a view, and solve() updates its grids in place)."""
+    return np.array(a[slab.row_offset:slab.row_offset + slab.rows], dtype=np.float32, order="C", copy=True)
 
 
 def put_owned(slab, dst, local):

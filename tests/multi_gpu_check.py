@@ -27,25 +27,16 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ok = True
     report = []
-    cases = [(512, 15, 20, 16, 2, 8, True), (1024, 40, 40, 32, 2, 8, True), (768, 7, 9, 8, 3, 4, False), (2048, 80, 80, 32, 2, 8, True)]
-    for n, kd, kp, halo, steps, T, graph in cases:
-        fields = rng_fields(n, 5000 + n, vel_cells=4.0)  # same seed on every rank
-        sl = slabmod.partition(n, world, halo, rank)
-        transport = os.environ.get("F2D_TRANSPORT", "auto")
-        tdev = torch.device("cuda", local_rank)
+    transport = os.environ.get("F2D_TRANSPORT", "auto")
+    tdev = torch.device("cuda", local_rank)
+
+    def make(sl, n, kd, kp, T, graph, cfl):
         uid = slabmod.broadcast_unique_id(dist, rank, device=tdev) if transport == "nccl" else None
-        s = slabmod.make_slab_solver(sl, n, uid, cfl_cells=6, device=local_rank, transport=transport, dist=dist, torch_device=tdev,
-                                     diffuse_iters=kd, project_iters=kp, temporal_block=T, divide_mode=f2d.DIV_F64, use_graph=graph)
-        loc = [slabmod.take(sl, a) for a in fields]
-        s.upload(*loc[:3])
-        s.set_sources(*loc[3:])
-        s.step(DIFFUSION_RATE, VISCOSITY, DT, steps)
-        s.sync()
-        out = s.download()
-        xch = slabmod.comm_exchanges(s)
-        s.close()
-        # gather owned rows on rank 0
-        glob = [np.zeros((n, n), np.float32) for _ in range(3)]
+        return slabmod.make_slab_solver(sl, n, uid, cfl_cells=cfl, device=local_rank, transport=transport, dist=dist, torch_device=tdev,
+                                        diffuse_iters=kd, project_iters=kp, temporal_block=T, divide_mode=f2d.DIV_F64, use_graph=graph)
+
+    def gather_owned(sl, n, halo, out):
+        glob = [None, None, None]
         for k in range(3):
             b, e = sl.local_own
             own = torch.from_numpy(np.ascontiguousarray(out[k][b:e])).cuda()
@@ -54,19 +45,105 @@ def main():
             dist.all_gather(parts, own) if len({p.shape for p in parts}) == 1 else _gather_uneven(dist, parts, own, rank, world)
             if rank == 0:
                 glob[k] = torch.cat(parts).cpu().numpy()
+        return glob
+
+    def any_rank_failed(failed):
+        t = torch.tensor([1 if failed else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return int(t.item()) == 1
+
+    def single_gpu(n, kd, kp, T, steps, fields, via_solve):
+        with f2d.FluidSolverB200(n, n, diffuse_iters=kd, project_iters=kp, temporal_block=T, divide_mode=f2d.DIV_F64,
+                                 device=local_rank) as one:
+            if via_solve:
+                h = [a.copy() for a in fields]
+                for _ in range(steps):
+                    one.solve(h[0], h[3], DIFFUSION_RATE, h[1], h[2], h[4], h[5], VISCOSITY, DT)
+                return h[:3]
+            one.upload(*fields[:3])
+            one.set_sources(*fields[3:])
+            one.step(DIFFUSION_RATE, VISCOSITY, DT, steps)
+            one.sync()
+            return one.download()
+
+    def judge(tag, glob, ref, steps, extra):
+        eu, ev, ed = err(glob[1], ref[1]), err(glob[2], ref[2]), err(glob[0], ref[0])
+        good = eu["n_diff"] == 0 and ev["n_diff"] == 0 and ed["rel_l2"] <= 2e-6 * steps and ed["max_abs"] <= 2e-5 * steps * max(1.0, float(np.abs(ref[0]).max()))
+        report.append(dict(case=tag, transport=transport, world=world, u=eu, v=ev, d=ed, ok=bool(good), **extra))
+        return good
+
+    # ---- 1. device-resident stepping: slabs == one GPU
+    cases = [(512, 15, 20, 16, 2, 8, True), (1024, 40, 40, 32, 2, 8, True), (768, 7, 9, 8, 3, 4, False), (2048, 80, 80, 32, 2, 8, True)]
+    for n, kd, kp, halo, steps, T, graph in cases:
+        fields = rng_fields(n, 5000 + n, vel_cells=4.0)  # same seed on every rank
+        sl = slabmod.partition(n, world, halo, rank)
+        s = make(sl, n, kd, kp, T, graph, 6)
+        loc = [slabmod.take(sl, a) for a in fields]
+        s.upload(*loc[:3])
+        s.set_sources(*loc[3:])
+        s.step(DIFFUSION_RATE, VISCOSITY, DT, steps)
+        s.sync()
+        out = s.download()
+        xch = slabmod.comm_exchanges(s)
+        s.close()
+        glob = gather_owned(sl, n, halo, out)
         if rank == 0:
-            with f2d.FluidSolverB200(n, n, diffuse_iters=kd, project_iters=kp, temporal_block=T, divide_mode=f2d.DIV_F64,
-                                     device=local_rank) as one:
-                one.upload(*fields[:3])
-                one.set_sources(*fields[3:])
-                one.step(DIFFUSION_RATE, VISCOSITY, DT, steps)
-                one.sync()
-                ref = one.download()
-            eu, ev, ed = err(glob[1], ref[1]), err(glob[2], ref[2]), err(glob[0], ref[0])
-            good = eu["n_diff"] == 0 and ev["n_diff"] == 0 and ed["rel_l2"] <= 2e-6 * steps and ed["max_abs"] <= 2e-5 * steps * max(1.0, float(np.abs(ref[0]).max()))
-            ok &= good
-            report.append(dict(transport=transport, n=n, kd=kd, kp=kp, halo=halo, steps=steps, T=T, graph=graph, world=world, exchanges=xch,
-                               u=eu, v=ev, d=ed, ok=bool(good)))
+            ok &= judge("step", glob, single_gpu(n, kd, kp, T, steps, fields, False), steps,
+                        dict(n=n, kd=kd, kp=kp, halo=halo, steps=steps, T=T, graph=graph, exchanges=xch))
+        dist.barrier()
+
+    # ---- 2. solve() per slab (uploads, the four parts of the step with their exchanges, downloads overlapped) == one GPU.
+    #         1024^2 slabs are >= 1 MiB and take the pipelined path; the host slabs carry stale halo rows between calls.
+    for n, kd, kp, halo, steps, T, graph in [(1024, 15, 20, 32, 2, 8, True), (1280, 24, 16, 32, 2, 8, False)]:
+        fields = rng_fields(n, 6000 + n, vel_cells=4.0)
+        sl = slabmod.partition(n, world, halo, rank)
+        s = make(sl, n, kd, kp, T, graph, 0)
+        h = [slabmod.take(sl, a) for a in fields]
+        for _ in range(steps):
+            s.solve(h[0], h[3], DIFFUSION_RATE, h[1], h[2], h[4], h[5], VISCOSITY, DT)
+        s.close()
+        glob = gather_owned(sl, n, halo, h[:3])
+        if rank == 0:
+            ok &= judge("solve", glob, single_gpu(n, kd, kp, T, steps, fields, True), steps,
+                        dict(n=n, kd=kd, kp=kp, halo=halo, steps=steps, T=T, graph=graph))
+        dist.barrier()
+
+    # ---- 3. the displacement bound (CFL) is verified on the device: never a silently wrong state.
+    #   a) ~20 rows per step with the default bound (halo - 1 = 31): equal to one GPU;
+    #   b) ~28 rows per step with a promised bound of 6 rows: the promise is broken -> f2d_sync fails on some rank;
+    #   c) ~45 rows per step: beyond what a 32-row halo can serve -> f2d_sync fails.
+    n, kd, kp, halo, T = 1024, 8, 8, 32, 8
+    for tag, cells, cfl, expect_error in (("cfl_ok_20_of_31", 20.0, 0, False), ("cfl_promise_6_broken", 28.0, 6, True),
+                                          ("cfl_beyond_halo", 45.0, 0, True)):
+        fields = list(rng_fields(n, 7000, vel_cells=cells))
+        # every cell moves 0.9 .. 1.0 x `cells` rows (v > 0 everywhere), so the rows next to a slab edge certainly do
+        fields[2] = (np.float32(0.95 * cells / (n * DT)) + np.float32(0.05) * fields[2]).astype(np.float32)
+        fields[5] = np.zeros_like(fields[5])
+        sl = slabmod.partition(n, world, halo, rank)
+        s = make(sl, n, kd, kp, T, True, cfl)
+        loc = [slabmod.take(sl, a) for a in fields]
+        s.upload(*loc[:3])
+        s.set_sources(*loc[3:])
+        failed = False
+        try:
+            s.step(DIFFUSION_RATE, VISCOSITY, DT, 1)
+            s.sync()
+        except f2d.F2DError as e:
+            failed = True
+            msg = str(e)
+        out = s.download()
+        s.close()
+        failed_any = any_rank_failed(failed)
+        if expect_error:
+            good = failed_any
+            if rank == 0:
+                report.append(dict(case=tag, transport=transport, world=world, error_reported=failed_any, ok=bool(good)))
+                ok &= good
+        else:
+            glob = gather_owned(sl, n, halo, out)
+            if rank == 0:
+                good = (not failed_any) and judge(tag, glob, single_gpu(n, kd, kp, T, 1, fields, False), 1, dict(n=n, cells=cells))
+                ok &= good
         dist.barrier()
     if rank == 0:
         print(json.dumps(report, indent=1))

@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, N-GPU call: slab == single GPU (step, pipelined solve(), CFL guard), then the 16384^2 bench line with its own 1-GPU base
+set -u
+N=${1:-2}
+TRANSPORTS=${2:-p2p}
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+for T in $TRANSPORTS; do
+  echo "=== check $T"; F2D_TRANSPORT=$T timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2971$N tests/multi_gpu_check.py > gpurun_out/multi_check_${T}_$N.log 2>&1; echo "exit $?"; grep -E "MULTI_GPU_CHECK|Error|error|timed out|\"case\"|\"ok\"" gpurun_out/multi_check_${T}_$N.log | paste - - | head -20
+  echo "=== bench $T"; F2D_TRANSPORT=$T timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2972$N bench.py --gpus $N --steps 10 --warmup 3 > gpurun_out/bench_16384_${N}gpu_$T.log 2>&1; echo "exit $?"; tail -n 1 gpurun_out/bench_16384_${N}gpu_$T.log | cut -c1-300
+done
