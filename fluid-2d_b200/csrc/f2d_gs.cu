@@ -269,8 +269,9 @@ void launch_advect_velocity_nofma(const Geom& g, const float* u0, const float* v
 // cpp:127-152 turned inside out (algorithm and per-cell functions: f2d_scatter_core.h).  Two passes, no atomics on
 // the data:
 //   k_scatter_keys     one thread per source: its landing cell as a linear index (or kNoKey), and the largest
-//                      displacement max(|dt0*u|, |dt0*v|) as the bit pattern of a non-negative float (integer max ==
-//                      float max there; a NaN compares above everything and widens the scan to the whole grid);
+//                      displacement max(|dt0*u|, |dt0*v|) over the sources that land inside the grid, as the bit pattern
+//                      of a non-negative float (integer max == float max there; a NaN compares above everything and
+//                      widens the scan to the whole grid);
 //   k_scatter_ordered  one thread per interior target: visits, in lexicographic order, every source whose displacement
 //                      can reach it (|di|, |dj| <= R = ceil(max displacement) + 1) and adds the share of those that
 //                      land on it.  Edge cells and corners are overwritten by the boundary pass that follows
@@ -284,8 +285,10 @@ __global__ void __launch_bounds__(256) k_scatter_keys(Geom g, const float* __res
         unsigned key = sc::kNoKey;
         if (i >= 1 && i <= g.rows - 2 && j >= 1 && j <= g.cols - 2) {
             const float uu = __ldg(u + o), vv = __ldg(v + o);
-            m = max(__float_as_uint(fabsf(__fmul_rn(dt0, uu))), __float_as_uint(fabsf(__fmul_rn(dt0, vv))));
             key = sc::source_key(g.rows, g.cols, g.pitch, i, j, uu, vv, dt0);
+            // only sources that land somewhere widen the scan: a skipped source (cpp:134) reaches no target, however
+            // far it would have travelled
+            if (key != sc::kNoKey) m = max(__float_as_uint(fabsf(__fmul_rn(dt0, uu))), __float_as_uint(fabsf(__fmul_rn(dt0, vv))));
         }
         keys[o] = key;
     }

@@ -60,6 +60,15 @@
 #define F2D_SHFL_AHEAD 0  // 1: west/east shuffles issued at the end of the previous row step (costs 2T live
                           // registers; slower since the row step became one basic block, profiles/ab_r01_run7_*.log)
 #endif
+#ifndef F2D_RHS_GEN
+#define F2D_RHS_GEN 1     // rhs in shared memory (T = 8): 1 = each rhs row is read back once per 3 levels and kept in
+                          // registers for the two following steps ("generations"); 0 = one LDS.128 per level and step
+#endif
+#ifndef F2D_RHS_MIRROR
+#define F2D_RHS_MIRROR 1  // rhs ring in shared memory: 1 = 16 slots + mirror of slots 0..7 (every row of a step at a
+                          // compile-time offset below one pointer, rows with bit 3 clear are written twice); 0 = plain
+                          // 16-slot ring, 8 KB-aligned, one "(row << 9) & mask | base" per read
+#endif
 
 namespace f2d {
 
@@ -78,7 +87,7 @@ __host__ __device__ constexpr int mrs(int x, int RS) { return ((x % RS) + RS) % 
 // kRingR slots and mirrors slots 0 .. kMirror-1 behind them (see slot_rd)
 constexpr int kRingR = 16;   // >= PFD + T + 2 for T <= 8
 constexpr int kMirror = 8;   // >= T
-__host__ __device__ constexpr int ring_r_slots(bool rhs_regs) { return rhs_regs ? kRingP : kRingR + kMirror; }
+__host__ __device__ constexpr int ring_r_slots(bool rhs_regs) { return rhs_regs ? kRingP : kRingR + (F2D_RHS_MIRROR ? kMirror : 0); }
 
 // Work decomposition.  Warps fall into two classes with different cost per row: class 0 = interior
 // strips, class 1 = the strips that hold a left/right domain edge column (extra edge fix per level).
@@ -150,9 +159,21 @@ __device__ __forceinline__ unsigned slot8(unsigned base, int row) { return (((un
 //   (r & 8) != 0: slots (r & 15) - 1 ... >= 0, the plain ring;
 //   (r & 8) == 0: from 16 + (r & 15) downwards -- mirrors first, then the plain slots 15, 14, ...
 // so level s reads its row at the compile-time offset -(s + 1) * 512 from slot_rd(base, r).
+#if F2D_RHS_MIRROR
 __device__ __forceinline__ unsigned slot_wr(unsigned base, int row) { return base + (((unsigned)row << 9) & ((kRingR - 1) << 9)); }
 __device__ __forceinline__ bool mirrored(int row) { return (row & kMirror) == 0; }
 __device__ __forceinline__ unsigned slot_rd(unsigned base, int r) { return slot_wr(base, r) + (mirrored(r) ? (unsigned)(kRingR << 9) : 0u); }
+// rhs row r - back (1 <= back <= T) given rd = slot_rd(base, r)
+__device__ __forceinline__ unsigned slot_back(unsigned, unsigned rd, int, int back) { return rd - (unsigned)(back << 9); }
+#else
+// plain ring, the block aligned to its own size (8 KB)
+__device__ __forceinline__ unsigned slot_wr(unsigned base, int row) { return (((unsigned)row << 9) & ((kRingR - 1) << 9)) | base; }
+__device__ __forceinline__ bool mirrored(int) { return false; }
+__device__ __forceinline__ unsigned slot_rd(unsigned, int r) { return (unsigned)r << 9; }
+__device__ __forceinline__ unsigned slot_back(unsigned base, unsigned rd, int, int back) {
+    return ((rd - (unsigned)(back << 9)) & ((kRingR - 1) << 9)) | base;
+}
+#endif
 static_assert(kMirror == 8 && kRingR == 16, "the mirror rule is bit 3 of the row index");
 
 // per-warp constants of one (strip, chunk)
@@ -189,7 +210,7 @@ struct Run {
 // EDGE: this warp's strip holds a domain edge column; interior strips are compiled without the edge-column fix.
 template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool FAST, bool EDGE, int RS, int NRH>
 __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int nsteps, float4 (&W)[T][3], float4 (&RH)[NRH],
-                                          float4& out_prev, float (&wl)[T], float (&er)[T], float4 (&UV)[2][3]) {
+                                          float4& out_prev, float (&wl)[T], float (&er)[T], float4 (&UV)[2][3], float4 (&XG)[3][3]) {
     static_assert(T <= kMirror, "the mirrored ring covers T <= 8 rows");
     // PIN_ZERO == 2: the first pressure pass with the divergence fused in (gpu.cu:164-177 + :376): the two
     // async rings carry u and v rows instead of iterate and rhs; the rhs row r-1 is computed on the fly
@@ -216,7 +237,9 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                     // slot twice; a branch here would split the row step into several basic blocks)
                     const unsigned w = slot_wr(cx.sr, rl);
                     cp_async16_s(w, cx.rhs + st.off_in, cx.cp_bytes);
+#if F2D_RHS_MIRROR
                     cp_async16_s(w + (mirrored(rl) ? (unsigned)(kRingR << 9) : 0u), cx.rhs + st.off_in, cx.cp_bytes);
+#endif
                 } else {
                     cp_async16_s(slot8(cx.sr, rl), cx.rhs + st.off_in, cx.cp_bytes);
                 }
@@ -304,7 +327,18 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
         const int s_top = cx.top_dom ? r - 2 : -1;           // level whose q == 1 (global top edge above it)
         const int s_bot = cx.bot_dom ? r - cx.re - 1 : -1;   // level whose q == re == global bottom edge row
         // rhs in shared memory: the rows r-1 .. r-T sit contiguously below this pointer (mirrored ring)
-        const unsigned rd = RHS_REGS ? 0u : slot_rd((FUSE || FSRC) ? cx.sd : cx.sr, r);
+        const unsigned rbase = (FUSE || FSRC) ? cx.sd : cx.sr;
+        const unsigned rd = RHS_REGS ? 0u : slot_rd(rbase, r);
+#if F2D_RHS_GEN
+        // Level s reads rhs row r-s-1, which level s-1 read one step earlier: levels are grouped in threes, the first
+        // level of a group loads its row (rows r-1, r-4, r-7) and the row stays in registers for the next two steps,
+        // where the second and third level of the group use it.  3 instead of T shared-memory reads per step; the
+        // generation index has the period of the window registers (3), so it is a compile-time constant.
+        if (!RHS_REGS) {
+#pragma unroll
+            for (int gq = 0; 3 * gq < T; ++gq) XG[gq][m3(k)] = lds128(slot_back(rbase, rd, r, 3 * gq + 1));
+        }
+#endif
 #pragma unroll
         for (int s = 0; s < T; ++s) {
             const int q = r - s - 1;
@@ -317,7 +351,11 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                 if (RHS_REGS)
                     rhs = RH[mrs(k - s - 1, RS)];
                 else
-                    rhs = lds128(rd - (unsigned)((s + 1) << 9));
+#if F2D_RHS_GEN
+                    rhs = XG[s / 3][m3(k - s % 3)];
+#else
+                    rhs = lds128(slot_back(rbase, rd, r, s + 1));
+#endif
                 float4 nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
                 // interior rows of an edge strip: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32), as
                 // two predicated selects (no branch) so that a whole row step stays one basic block
@@ -366,14 +404,14 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
 template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool EDGE, int RS, int NRH>
 __device__ __forceinline__ void march(const Ctx& cx, Run& st, int nsteps, int top_lo, int top_hi, int bot_lo, int bot_hi,
                                       float4 (&W)[T][3], float4 (&RH)[NRH], float4& out_prev, float (&wl)[T], float (&er)[T],
-                                      float4 (&UV)[2][3]) {
+                                      float4 (&UV)[2][3], float4 (&XG)[3][3]) {
     for (int rb = 0; rb < nsteps; rb += RS) {
         const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
         const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
         if (!edge_block)
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, out_prev, wl, er, UV);
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, out_prev, wl, er, UV, XG);
         else
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, out_prev, wl, er, UV);
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, out_prev, wl, er, UV, XG);
     }
 }
 
@@ -432,7 +470,9 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
         // [rhs rings of warp 0 .. wpc-1][landing rings ...]: a landing ring is 4 KB and 4 KB-aligned ("(row << 9) & mask
         // | base" addresses a slot with two integer instructions); the mirrored rhs ring is 12 KB per warp
         constexpr unsigned RB = ring_r_slots(RHS_REGS) * kLanes * 16u, PB = kRingP * kLanes * 16u;
-        const unsigned s0 = ((unsigned)__cvta_generic_to_shared(smem) + PB - 1u) & ~(PB - 1u);
+        constexpr unsigned AL = (!F2D_RHS_MIRROR && !RHS_REGS) ? RB : PB;  // a plain rhs ring is aligned to its own size
+        static_assert(AL >= PB && (AL & (AL - 1u)) == 0u, "ring alignment");
+        const unsigned s0 = ((unsigned)__cvta_generic_to_shared(smem) + AL - 1u) & ~(AL - 1u);
         if (PIN_ZERO >= 2) {
             // fused divergence / add_sources: [computed rhs ring (RB) x wpc][landing ring (PB) x wpc][landing ring (PB) x wpc]
             cx.sd = s0 + (unsigned)warp_in_cta * RB + (unsigned)lane * 16u;
@@ -471,8 +511,9 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
     float wl[T], er[T];
     float4 UV[2][3];
+    float4 XG[3][3];
 #pragma unroll
-    for (int m = 0; m < 3; ++m) UV[0][m] = UV[1][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < 3; ++m) UV[0][m] = UV[1][m] = XG[0][m] = XG[1][m] = XG[2][m] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < T; ++s) {
         wl[s] = er[s] = 0.f;
@@ -505,9 +546,9 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     st.off_out = (cx.rs - T) * cx.pitch;
 
     if (!cx.edge_warp)
-        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV);
+        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
     else
-        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV);
+        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
     cp_async_wait<0>();
 }
 
@@ -551,7 +592,7 @@ cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& t
     wpc = std::min(wpc, 4);  // __launch_bounds__(128, ...)
     // rhs ring(s) + iterate landing ring(s) per warp (see the kernel's layout comment) + 4 KB of alignment slack
     const size_t smem = (size_t)wpc * (ring_r_slots(RHS_REGS) + kRingP + (PIN_ZERO >= 2 ? kRingP : 0)) * kLanes * sizeof(float4) +
-                        (size_t)kRingP * kLanes * sizeof(float4);
+                        (size_t)((!F2D_RHS_MIRROR && !RHS_REGS) ? kRingR : kRingP) * kLanes * sizeof(float4);
     // per device (function attributes live in the device's context) and per CTA size; a failed opt-in to more than
     // 48 KB of dynamic shared memory or a failed occupancy query is reported here, not at some later launch
     static int occ_cache_dev[16][9] = {};

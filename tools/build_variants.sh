@@ -3,6 +3,11 @@
 set -e
 cd "$(dirname "$0")/../fluid-2d_b200/csrc"
 build() { name=$1; shift; make -j8 OUT="$PWD/../libf2d_$name.so" BUILD="$PWD/build_$name" VARIANT="$*" > /dev/null; echo "built libf2d_$name.so ($*)"; }
-build v1 -DF2D_RING_OR=1 -DF2D_SHFL_AHEAD=1
-build v2 -DF2D_RING_OR=0 -DF2D_SHFL_AHEAD=1
-build v3 -DF2D_RING_OR=0 -DF2D_SHFL_AHEAD=0
+for v in "$@"; do
+  case $v in
+    g0m1) build g0m1 -DF2D_RHS_GEN=0 -DF2D_RHS_MIRROR=1 ;;   # round-2 v3 kernel: one rhs LDS.128 per level and step
+    g1m1) build g1m1 -DF2D_RHS_GEN=1 -DF2D_RHS_MIRROR=1 ;;
+    g1m0) build g1m0 -DF2D_RHS_GEN=1 -DF2D_RHS_MIRROR=0 ;;
+    *) echo "unknown variant $v"; exit 1 ;;
+  esac
+done
