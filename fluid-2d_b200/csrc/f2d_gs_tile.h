@@ -244,7 +244,10 @@ F2D_HD void step_fetch(StepRegs& g) {
 F2D_HD void tile_step_init(const Tile& t, float* tile, const float* rt, int lane, StepRegs& g) {
     const int ll = (lane < t.nr) ? lane : 0;  // rows beyond the band shadow row 0 and never store
     g.west = tile[(ll + 1) * kTP];
-    g.cell = tile + (ll + 1) * kTP + (1 - lane);  // column q = step - lane, step = 0
+    // column q = step - lane, step = 0.  Lanes without a row (lane >= nr) shadow row 0 two columns further left: they
+    // then only ever read cells that lanes 0 / 1 wrote in an EARLIER step (a step ends with __syncwarp), never the
+    // cell being written in the same step (compute-sanitizer racecheck is clean for bands of one or two rows, too)
+    g.cell = tile + (ll + 1) * kTP + (1 - lane) - ((lane < t.nr) ? 0 : 2);
     g.rp = rt + ll * kTileCols - lane;
     g.tp = tile + (1 - lane);
     step_fetch(g);

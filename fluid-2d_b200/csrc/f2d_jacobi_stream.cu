@@ -61,8 +61,11 @@
                           // registers; slower since the row step became one basic block, profiles/ab_r01_run7_*.log)
 #endif
 #ifndef F2D_RHS_GEN
-#define F2D_RHS_GEN 1     // rhs in shared memory (T = 8): 1 = each rhs row is read back once per 3 levels and kept in
+#define F2D_RHS_GEN 0     // rhs in shared memory (T = 8): 1 = each rhs row is read back once per 3 levels and kept in
                           // registers for the two following steps ("generations"); 0 = one LDS.128 per level and step
+#endif
+#ifndef F2D_PRESSURE_SCALED
+#define F2D_PRESSURE_SCALED 1  // pressure levels carried as 4^s * p (see relax_row): 4 instead of 5 operations per cell-sweep
 #endif
 #ifndef F2D_RHS_MIRROR
 #define F2D_RHS_MIRROR 1  // rhs ring in shared memory: 1 = 16 slots + mirror of slots 0..7 (every row of a step at a
@@ -120,15 +123,61 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-template <bool DIFFUSE, int DIVMODE>
+// ---- pass chaining (several passes in one launch): progress counters in global memory
+__device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(unsigned* p, unsigned v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long wall_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// chunk of class `c` that owns row y (inverse of the y0 / y1 formulas in the kernel)
+__device__ __forceinline__ int chunk_of(const StreamPlan& plan, int c, int y) {
+    return min(plan.chunks[c] - 1, (y + plan.edge_trim[c]) / plan.chunk_rows[c]);
+}
+
+// Pressure sweep (gpu.cu:187-188): p' = ((((d + pE) + pW) + pS) + pN) * 0.25f.  The multiplication by 0.25 is exact, so
+// a pass can carry level s as t_s = 4^s * p_s:  t_{s+1} = (((FMA(d, 4^s, tE) + tW) + tS) + tN)  -- FMA(d, 4^s, tE) rounds
+// 4^s * (d + pE) exactly as the reference rounds d + pE, and every later sum is the reference's sum times 4^s -- and
+// multiply the last level by 4^-T once.  4T + 1 instead of 5T operations per cell and pass, bit-identical to the
+// reference unless 0.25 * sum is subnormal (|p| < 2^-126: the reference then rounds to the subnormal grid at every
+// sweep, this only at the end of the pass) or 4^T * p overflows (|p| > 2^111).
+__host__ __device__ constexpr float level_scale(int s) { return (float)(1u << (2 * s)); }
+__host__ __device__ constexpr float pass_unscale(int T) { return 1.0f / (float)(1u << (2 * T)); }
+__device__ __forceinline__ float pressure_scaled(float dv, float cs, float e, float w, float s, float n) {
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmaf_rn(dv, cs, e), w), s), n);
+}
+
+// level S of a pass of T: rows a (north), b (centre), c (south) of level S -> the centre row of level S + 1
+// (S is a constant after unrolling, so the scale factors fold into immediates)
+template <bool DIFFUSE, int DIVMODE, int T>
 __device__ __forceinline__ float4 relax_row(const float4& a, const float4& b, const float4& c, float l, float rt,
-                                            const float4& rhs, const DiffuseCoef& k) {
+                                            const float4& rhs, const DiffuseCoef& k, int S) {
     float4 o;
     if (DIFFUSE) {
         o.x = diffuse_update<DIVMODE>(l, b.y, a.x, c.x, rhs.x, k);
         o.y = diffuse_update<DIVMODE>(b.x, b.z, a.y, c.y, rhs.y, k);
         o.z = diffuse_update<DIVMODE>(b.y, b.w, a.z, c.z, rhs.z, k);
         o.w = diffuse_update<DIVMODE>(b.z, rt, a.w, c.w, rhs.w, k);
+    } else if (F2D_PRESSURE_SCALED) {
+        const float cs = level_scale(S);
+        o.x = pressure_scaled(rhs.x, cs, b.y, l, c.x, a.x);
+        o.y = pressure_scaled(rhs.y, cs, b.z, b.x, c.y, a.y);
+        o.z = pressure_scaled(rhs.z, cs, b.w, b.y, c.z, a.z);
+        o.w = pressure_scaled(rhs.w, cs, rt, b.z, c.w, a.w);
+        if (S == T - 1) {
+            const float un = pass_unscale(T);
+            o.x = __fmul_rn(o.x, un);
+            o.y = __fmul_rn(o.y, un);
+            o.z = __fmul_rn(o.z, un);
+            o.w = __fmul_rn(o.w, un);
+        }
     } else {
         o.x = pressure_update(rhs.x, b.y, l, c.x, a.x);
         o.y = pressure_update(rhs.y, b.z, b.x, c.y, a.y);
@@ -137,17 +186,22 @@ __device__ __forceinline__ float4 relax_row(const float4& a, const float4& b, co
     }
     return o;
 }
+// factor that takes a corner value carried at the scale of level S to the scale of the row level S produces
+template <bool DIFFUSE, int T>
+__host__ __device__ constexpr float corner_carry(int S) {
+    return (DIFFUSE || !F2D_PRESSURE_SCALED) ? 1.0f : (S == T - 1 ? 1.0f / level_scale(S) : 4.0f);
+}
 
 // edge row from the adjacent interior row of the same level; corner cells keep `keep`
-__device__ __forceinline__ float4 edge_row(const float4& inner, const float4& keep, bool neg, bool has_left,
+__device__ __forceinline__ float4 edge_row(const float4& inner, const float4& keep, float keep_mul, bool neg, bool has_left,
                                            bool has_right) {
     float4 o;
     o.x = apply_sign(inner.x, neg);
     o.y = apply_sign(inner.y, neg);
     o.z = apply_sign(inner.z, neg);
     o.w = apply_sign(inner.w, neg);
-    if (has_left) o.x = keep.x;
-    if (has_right) o.w = keep.w;
+    if (has_left) o.x = __fmul_rn(keep.x, keep_mul);  // exact: keep_mul is a power of four (1 for diffuse)
+    if (has_right) o.w = __fmul_rn(keep.w, keep_mul);
     return o;
 }
 
@@ -356,7 +410,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
 #else
                     rhs = lds128(slot_back(rbase, rd, r, s + 1));
 #endif
-                float4 nw = relax_row<DIFFUSE, DIVMODE>(a, b, c, l, rt, rhs, cx.coef);
+                float4 nw = relax_row<DIFFUSE, DIVMODE, T>(a, b, c, l, rt, rhs, cx.coef, s);
                 // interior rows of an edge strip: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32), as
                 // two predicated selects (no branch) so that a whole row step stays one basic block
                 if (EDGE) {
@@ -370,7 +424,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                     if (cx.own_x && q >= cx.y0 && q < cx.y1) st_global_f4(cx.next + st.off_out, nw);
                 }
                 if (!FAST && s == s_top) {  // global top edge row of the same level (corners kept)
-                    const float4 e = edge_row(nw, a, cx.neg_r, hl, hr);
+                    const float4 e = edge_row(nw, a, corner_carry<DIFFUSE, T>(s), cx.neg_r, hl, hr);
                     if (s + 1 < T)
                         W[sn][sa] = e;
                     else if (cx.own_x && cx.y0 == 0)
@@ -378,7 +432,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                 }
             } else if (!FAST && s == s_bot && q >= cx.rs + 1) {  // global bottom edge row
                 const float4 inner = (s + 1 < T) ? W[sn][sa] : out_prev;
-                const float4 e = edge_row(inner, W[s][sm], cx.neg_r, hl, hr);
+                const float4 e = edge_row(inner, W[s][sm], corner_carry<DIFFUSE, T>(s), cx.neg_r, hl, hr);
                 if (s + 1 < T)
                     W[sn][sm] = e;
                 else if (cx.own_x && q >= cx.y0 && q < cx.y1)
@@ -415,12 +469,33 @@ __device__ __forceinline__ void march(const Ctx& cx, Run& st, int nsteps, int to
     }
 }
 
+// Several passes in ONE launch (PIN_ZERO == 0 only; sync.npasses > 1).  A warp keeps its (strip, chunk) for all passes
+// and ping-pongs between the two iterate buffers.  Pass p of a warp reads what pass p-1 of the <= 3 x 3 neighbouring
+// (strip, chunk) warps wrote -- and overwrites what they read in pass p-1 -- so it may start as soon as THOSE warps have
+// published pass p-1: one monotone progress counter per warp in global memory (written after a device-scope fence,
+// polled by one lane per neighbour), no grid-wide barrier, no launch ramp / drain between passes.  Counter values are
+// generation + pass: the generation word lives next to the counters and is advanced by the last warp that finishes a
+// launch, so the same kernel node replays inside a CUDA graph without any reset.  The launch is one wave by
+// construction (the planner sizes it from the occupancy), so every warp a wait refers to is resident or finished; every
+// wait is bounded in wall-clock time and raises the error word f2d_sync reports instead of hanging.
+struct StreamSync {
+    unsigned* flags;   // batch.n * stride progress counters
+    unsigned* ctl;     // [0] generation, [1] warps finished in this launch
+    unsigned* err;     // raised when a wait timed out (one word per solver, reported by f2d_sync)
+    int npasses;       // passes chained in this launch (1: plain single pass, nothing below is touched)
+    unsigned stride;   // counters per field (>= warps per field)
+    unsigned total;    // warps taking part (all fields)
+    unsigned long long timeout_ns;
+};
+enum { SY_GEN = 0, SY_DONE = 1 };
+
 // MINB = resident CTAs (of 128 threads) per SM the register allocator must allow
 template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch batch, StreamPlan plan) {
+__global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch batch, StreamPlan plan, StreamSync sync) {
     constexpr int HALO = halo_of(T);
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;  // unroll factor of the row loop
     constexpr int NRH = RHS_REGS ? RS : 1;
+    constexpr bool CHAIN = (PIN_ZERO == 0);      // the plain relaxation pass is the only variant that chains passes
     extern __shared__ float4 smem[];
 
     const int lane = threadIdx.x & 31;
@@ -506,50 +581,111 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     const int top_lo = cx.top_dom ? 2 : 1 << 30, top_hi = cx.top_dom ? T + 1 : -1;
     const int bot_lo = cx.bot_dom ? cx.re + 1 : 1 << 30, bot_hi = cx.bot_dom ? cx.re + T : -1;
 
-    float4 W[T][3];
-    float4 RH[NRH];
-    float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
-    float wl[T], er[T];
-    float4 UV[2][3];
-    float4 XG[3][3];
-#pragma unroll
-    for (int m = 0; m < 3; ++m) UV[0][m] = UV[1][m] = XG[0][m] = XG[1][m] = XG[2][m] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int s = 0; s < T; ++s) {
-        wl[s] = er[s] = 0.f;
-#pragma unroll
-        for (int m = 0; m < 3; ++m) W[s][m] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int m = 0; m < NRH; ++m) RH[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-    // ---- prologue: rows rs .. rs+PFD-1 in flight
-    constexpr bool RHS_LANDS_MIRRORED = !RHS_REGS && PIN_ZERO < 2;
-#pragma unroll
-    for (int p = 0; p < kPFD; ++p) {
-        const int rl = cx.rs + p;
-        if (rl <= cx.re) {
-            const size_t off = (size_t)rl * cx.pitch;
-            if (PIN_ZERO != 1) cp_async16_s(slot8(cx.sp, rl), cx.prev + off, cx.cp_bytes);
-            if (RHS_LANDS_MIRRORED) {
-                const unsigned w = slot_wr(cx.sr, rl);
-                cp_async16_s(w, cx.rhs + off, cx.cp_bytes);
-                if (mirrored(rl)) cp_async16_s(w + (kRingR << 9), cx.rhs + off, cx.cp_bytes);
-            } else {
-                cp_async16_s(slot8(cx.sr, rl), cx.rhs + off, cx.cp_bytes);
+    const int npasses = CHAIN ? sync.npasses : 1;
+    for (int pass = 0; pass < npasses; ++pass) {
+        if (CHAIN && pass > 0) {
+            // ---- wait for pass - 1 of the neighbouring (strip, chunk) warps: lanes 0..29 take one counter each, strip
+            //      strip-1+lane/10, chunk c_lo+lane%10 of that strip's class (a chunk range longer than 10 cannot occur:
+            //      chunks own >= 2T rows and the two classes' heights differ by the cost ratio only)
+            const unsigned* nb = nullptr;
+            {
+                const int s2 = strip - 1 + lane / 10;
+                if (lane < 30 && s2 >= 0 && s2 < plan.strips) {
+                    const bool edge2 = plan.n_edge_strips > 0 && (s2 == 0 || s2 == plan.strips - 1);
+                    const int c2 = edge2 ? 1 : 0;
+                    const int c = chunk_of(plan, c2, cx.rs) + lane % 10;
+                    if (c <= chunk_of(plan, c2, cx.re)) {
+                        const int w2 = edge2 ? plan.warps_int + c * plan.n_edge_strips + (s2 == 0 ? 0 : plan.n_edge_strips - 1)
+                                             : c * (plan.strips - plan.n_edge_strips) + s2 - (plan.n_edge_strips ? 1 : 0);
+                        if (w2 != gw) nb = sync.flags + (size_t)blockIdx.y * sync.stride + w2;
+                    }
+                }
             }
+            const unsigned target = ld_flag(sync.ctl + SY_GEN) + (unsigned)pass;  // neighbours have finished `pass` passes
+            bool ok = (nb == nullptr) || (int)(ld_flag(nb) - target) >= 0;
+            if (!__all_sync(0xffffffffu, ok)) {
+                const unsigned long long t0 = wall_ns();
+                unsigned it = 0;
+                do {
+                    __nanosleep(64);
+                    ok = (nb == nullptr) || (int)(ld_flag(nb) - target) >= 0;
+                    const bool give_up = (++it & 1023u) == 0u && (wall_ns() - t0 > sync.timeout_ns || ld_flag(sync.err) != 0u);
+                    if (__any_sync(0xffffffffu, give_up)) {
+                        if (lane == 0) atomicExch(sync.err, 1u);
+                        break;
+                    }
+                } while (!__all_sync(0xffffffffu, ok));
+            }
+            __threadfence();  // acquire: the rows read below were written before the counters were published
+            // ping-pong: pass p reads what pass p-1 wrote
+            const float* in = ((pass & 1) ? fld.next : fld.alt) + jsafe;
+            float* out = ((pass & 1) ? fld.alt : fld.next) + jsafe;
+            cx.prev = in;
+            cx.next = out;
+            asm volatile("" : "+l"(cx.prev), "+l"(cx.next));
         }
-        cp_async_commit();
-    }
-    Run st;
-    st.off_in = (cx.rs + kPFD) * cx.pitch;
-    st.off_out = (cx.rs - T) * cx.pitch;
 
-    if (!cx.edge_warp)
-        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
-    else
-        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
-    cp_async_wait<0>();
+        float4 W[T][3];
+        float4 RH[NRH];
+        float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
+        float wl[T], er[T];
+        float4 UV[2][3];
+        float4 XG[3][3];
+#pragma unroll
+        for (int m = 0; m < 3; ++m) UV[0][m] = UV[1][m] = XG[0][m] = XG[1][m] = XG[2][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < T; ++s) {
+            wl[s] = er[s] = 0.f;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) W[s][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int m = 0; m < NRH; ++m) RH[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        // ---- prologue: rows rs .. rs+PFD-1 in flight
+        constexpr bool RHS_LANDS_MIRRORED = !RHS_REGS && PIN_ZERO < 2;
+#pragma unroll
+        for (int p = 0; p < kPFD; ++p) {
+            const int rl = cx.rs + p;
+            if (rl <= cx.re) {
+                const size_t off = (size_t)rl * cx.pitch;
+                if (PIN_ZERO != 1) cp_async16_s(slot8(cx.sp, rl), cx.prev + off, cx.cp_bytes);
+                if (RHS_LANDS_MIRRORED) {
+                    const unsigned w = slot_wr(cx.sr, rl);
+                    cp_async16_s(w, cx.rhs + off, cx.cp_bytes);
+                    if (mirrored(rl)) cp_async16_s(w + (kRingR << 9), cx.rhs + off, cx.cp_bytes);
+                } else {
+                    cp_async16_s(slot8(cx.sr, rl), cx.rhs + off, cx.cp_bytes);
+                }
+            }
+            cp_async_commit();
+        }
+        Run st;
+        st.off_in = (cx.rs + kPFD) * cx.pitch;
+        st.off_out = (cx.rs - T) * cx.pitch;
+
+        if (!cx.edge_warp)
+            march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
+        else
+            march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
+        cp_async_wait<0>();
+
+        if (CHAIN && npasses > 1) {
+            // publish: this warp's rows of pass `pass` are visible device-wide before the counter moves
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_flag(sync.flags + (size_t)blockIdx.y * sync.stride + gw, ld_flag(sync.ctl + SY_GEN) + (unsigned)pass + 1u);
+        }
+    }
+    if (CHAIN && npasses > 1 && lane == 0) {
+        // the last warp out advances the generation for the next launch that uses this sync block
+        const unsigned gen = ld_flag(sync.ctl + SY_GEN);
+        __threadfence();
+        if (atomicAdd(sync.ctl + SY_DONE, 1u) == sync.total - 1u) {
+            st_flag(sync.ctl + SY_DONE, 0u);
+            st_flag(sync.ctl + SY_GEN, gen + (unsigned)npasses);
+        }
+    }
 }
 
 // Host-side planner.  One wave, every resident warp slot busy, all warps finishing together:
@@ -585,7 +721,8 @@ inline ClassPlan plan_class(int rows, int T, int RS, double cost_budget, double 
 }
 
 template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, int MINB>
-cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, int sm_count, cudaStream_t st) {
+cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, int sm_count, cudaStream_t st, int npasses,
+                       const StreamChain& chain) {
     auto kern = k_jacobi_stream<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, MINB>;
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;
     int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
@@ -649,26 +786,40 @@ cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& t
     plan.warps_int = n_int * ci.chunks;
     const long total_warps = (long)plan.warps_int + (long)plan.n_edge_strips * ce.chunks;
     dim3 grid((unsigned)((total_warps + wpc - 1) / wpc), b.n);
-    kern<<<grid, wpc * 32, smem, st>>>(g, b, plan);
+    StreamSync sync = {nullptr, nullptr, nullptr, 1, 0u, 0u, 0ull};
+    if (npasses > 1) {
+        // chained passes: every warp of the launch must be resident at once (one wave) and needs a progress counter
+        if (PIN_ZERO != 0 || chain.block == nullptr || chain.err == nullptr) return cudaErrorInvalidValue;
+        if ((long)grid.x * b.n > (long)occ_cache[wpc] * sm_count) return cudaErrorCooperativeLaunchTooLarge;
+        if ((size_t)total_warps * b.n + kChainCtlWords > chain.words) return cudaErrorInvalidValue;
+        sync.ctl = chain.block;
+        sync.err = chain.err;
+        sync.flags = chain.block + kChainCtlWords;
+        sync.npasses = npasses;
+        sync.stride = (unsigned)total_warps;
+        sync.total = (unsigned)(total_warps * b.n);
+        sync.timeout_ns = chain.timeout_ns;
+    }
+    kern<<<grid, wpc * 32, smem, st>>>(g, b, plan, sync);
     return cudaGetLastError();
 }
 
 template <int T, bool RHS_REGS, int MINB>
 cudaError_t launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, const StreamTuning& tune, int sm_count,
-                     cudaStream_t st) {
+                     cudaStream_t st, int npasses, const StreamChain& chain) {
     if (!diffuse) {
         if (b.f[0].aux != nullptr)  // first pressure pass with the divergence fused in: prev = u, rhs = v
-            return launch_one<T, false, F2D_DIV_F64, 2, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-        if (b.f[0].prev == nullptr) return launch_one<T, false, F2D_DIV_F64, 1, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-        return launch_one<T, false, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+            return launch_one<T, false, F2D_DIV_F64, 2, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
+        if (b.f[0].prev == nullptr) return launch_one<T, false, F2D_DIV_F64, 1, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
+        return launch_one<T, false, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
     }
     if (divmode == F2D_DIV_F64) {
         if (b.f[0].aux != nullptr)  // first diffuse pass with add_sources fused in: prev = field, rhs = source
-            return launch_one<T, true, F2D_DIV_F64, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-        return launch_one<T, true, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+            return launch_one<T, true, F2D_DIV_F64, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
+        return launch_one<T, true, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
     }
-    if (b.f[0].aux != nullptr) return launch_one<T, true, F2D_DIV_F32_CORR, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
-    return launch_one<T, true, F2D_DIV_F32_CORR, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+    if (b.f[0].aux != nullptr) return launch_one<T, true, F2D_DIV_F32_CORR, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
+    return launch_one<T, true, F2D_DIV_F32_CORR, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
 }
 
 }  // namespace
@@ -678,17 +829,18 @@ bool stream_supported(const Geom& g, int T) {
     return g.cols >= 4 && (g.cols % 4 == 0) && (g.pitch % 4 == 0) && g.rows >= 3;
 }
 
-cudaError_t launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
-                                 const StreamTuning& tune, int sm_count, cudaStream_t st) {
-    (void)sweeps;  // == T: the step driver decomposes K into passes of 8/4/2/1 sweeps
+cudaError_t launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int npasses,
+                                 const StreamTuning& tune, int sm_count, cudaStream_t st, const StreamChain& chain) {
+    // npasses passes of T sweeps each in one launch (the step driver decomposes K into passes of 8/4/2/1 sweeps);
+    // npasses > 1 needs a plain pass (no fused first pass), b.f[i].alt and a sync block
     // T = 8 keeps the right-hand side in the smem ring (unroll 3): with a register ring the unrolled
     // row loop (9 x 8 levels) outgrows the instruction cache.  MINB = resident 128-thread CTAs per SM the register
     // allocator must allow: T = 8 -> 3 (168 regs), T = 4 -> 4 (128 regs).
     switch (T) {
-        case 1: return launch_T<1, true, 6>(g, b, diffuse, divmode, tune, sm_count, st);
-        case 2: return launch_T<2, true, 6>(g, b, diffuse, divmode, tune, sm_count, st);
-        case 4: return launch_T<4, true, 4>(g, b, diffuse, divmode, tune, sm_count, st);
-        default: return launch_T<8, false, 3>(g, b, diffuse, divmode, tune, sm_count, st);
+        case 1: return launch_T<1, true, 6>(g, b, diffuse, divmode, tune, sm_count, st, npasses, chain);
+        case 2: return launch_T<2, true, 6>(g, b, diffuse, divmode, tune, sm_count, st, npasses, chain);
+        case 4: return launch_T<4, true, 4>(g, b, diffuse, divmode, tune, sm_count, st, npasses, chain);
+        default: return launch_T<8, false, 3>(g, b, diffuse, divmode, tune, sm_count, st, npasses, chain);
     }
 }
 
