@@ -51,6 +51,10 @@
 //     4096^2 -- the packed operations occupy the FMA pipe for two cycles each (no pipe time saved,
 //     profiles/ubench_fp32x2_r02.jsonl), pair assembly costs two moves per row and level, and the 168-register
 //     budget spills (git 7a65d0d; profiles/ncu_jacobi_*_T8_r02_packed_fp32x2.md).
+//   * Also built, measured and dropped in round 2 (git history; numbers in profiles/ab_r02_*.log): (a) the passes of one
+//     relaxation chained inside ONE launch, each warp waiting only for the progress counters of its 3 x 3 neighbouring
+//     (strip, chunk) warps: the device-scope fence + counter round trip per pass costs as much as the launch it replaces
+//     inside a CUDA graph (4096^2 step 3.44 vs 3.37 ms, 256^2 0.148 vs 0.109 ms); (b) F2D_RHS_GEN=1, below.
 #include <algorithm>
 
 #include "f2d_kernels.cuh"
@@ -121,25 +125,6 @@ __device__ __forceinline__ void st_global_f4(float* p, const float4& v) {
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-// ---- pass chaining (several passes in one launch): progress counters in global memory
-__device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_flag(unsigned* p, unsigned v) {
-    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long wall_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// chunk of class `c` that owns row y (inverse of the y0 / y1 formulas in the kernel)
-__device__ __forceinline__ int chunk_of(const StreamPlan& plan, int c, int y) {
-    return min(plan.chunks[c] - 1, (y + plan.edge_trim[c]) / plan.chunk_rows[c]);
 }
 
 // Pressure sweep (gpu.cu:187-188): p' = ((((d + pE) + pW) + pS) + pN) * 0.25f.  The multiplication by 0.25 is exact, so
@@ -469,33 +454,12 @@ __device__ __forceinline__ void march(const Ctx& cx, Run& st, int nsteps, int to
     }
 }
 
-// Several passes in ONE launch (PIN_ZERO == 0 only; sync.npasses > 1).  A warp keeps its (strip, chunk) for all passes
-// and ping-pongs between the two iterate buffers.  Pass p of a warp reads what pass p-1 of the <= 3 x 3 neighbouring
-// (strip, chunk) warps wrote -- and overwrites what they read in pass p-1 -- so it may start as soon as THOSE warps have
-// published pass p-1: one monotone progress counter per warp in global memory (written after a device-scope fence,
-// polled by one lane per neighbour), no grid-wide barrier, no launch ramp / drain between passes.  Counter values are
-// generation + pass: the generation word lives next to the counters and is advanced by the last warp that finishes a
-// launch, so the same kernel node replays inside a CUDA graph without any reset.  The launch is one wave by
-// construction (the planner sizes it from the occupancy), so every warp a wait refers to is resident or finished; every
-// wait is bounded in wall-clock time and raises the error word f2d_sync reports instead of hanging.
-struct StreamSync {
-    unsigned* flags;   // batch.n * stride progress counters
-    unsigned* ctl;     // [0] generation, [1] warps finished in this launch
-    unsigned* err;     // raised when a wait timed out (one word per solver, reported by f2d_sync)
-    int npasses;       // passes chained in this launch (1: plain single pass, nothing below is touched)
-    unsigned stride;   // counters per field (>= warps per field)
-    unsigned total;    // warps taking part (all fields)
-    unsigned long long timeout_ns;
-};
-enum { SY_GEN = 0, SY_DONE = 1 };
-
 // MINB = resident CTAs (of 128 threads) per SM the register allocator must allow
 template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, int MINB>
-__global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch batch, StreamPlan plan, StreamSync sync) {
+__global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch batch, StreamPlan plan) {
     constexpr int HALO = halo_of(T);
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;  // unroll factor of the row loop
     constexpr int NRH = RHS_REGS ? RS : 1;
-    constexpr bool CHAIN = (PIN_ZERO == 0);      // the plain relaxation pass is the only variant that chains passes
     extern __shared__ float4 smem[];
 
     const int lane = threadIdx.x & 31;
@@ -581,111 +545,50 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     const int top_lo = cx.top_dom ? 2 : 1 << 30, top_hi = cx.top_dom ? T + 1 : -1;
     const int bot_lo = cx.bot_dom ? cx.re + 1 : 1 << 30, bot_hi = cx.bot_dom ? cx.re + T : -1;
 
-    const int npasses = CHAIN ? sync.npasses : 1;
-    for (int pass = 0; pass < npasses; ++pass) {
-        if (CHAIN && pass > 0) {
-            // ---- wait for pass - 1 of the neighbouring (strip, chunk) warps: lanes 0..29 take one counter each, strip
-            //      strip-1+lane/10, chunk c_lo+lane%10 of that strip's class (a chunk range longer than 10 cannot occur:
-            //      chunks own >= 2T rows and the two classes' heights differ by the cost ratio only)
-            const unsigned* nb = nullptr;
-            {
-                const int s2 = strip - 1 + lane / 10;
-                if (lane < 30 && s2 >= 0 && s2 < plan.strips) {
-                    const bool edge2 = plan.n_edge_strips > 0 && (s2 == 0 || s2 == plan.strips - 1);
-                    const int c2 = edge2 ? 1 : 0;
-                    const int c = chunk_of(plan, c2, cx.rs) + lane % 10;
-                    if (c <= chunk_of(plan, c2, cx.re)) {
-                        const int w2 = edge2 ? plan.warps_int + c * plan.n_edge_strips + (s2 == 0 ? 0 : plan.n_edge_strips - 1)
-                                             : c * (plan.strips - plan.n_edge_strips) + s2 - (plan.n_edge_strips ? 1 : 0);
-                        if (w2 != gw) nb = sync.flags + (size_t)blockIdx.y * sync.stride + w2;
-                    }
-                }
-            }
-            const unsigned target = ld_flag(sync.ctl + SY_GEN) + (unsigned)pass;  // neighbours have finished `pass` passes
-            bool ok = (nb == nullptr) || (int)(ld_flag(nb) - target) >= 0;
-            if (!__all_sync(0xffffffffu, ok)) {
-                const unsigned long long t0 = wall_ns();
-                unsigned it = 0;
-                do {
-                    __nanosleep(64);
-                    ok = (nb == nullptr) || (int)(ld_flag(nb) - target) >= 0;
-                    const bool give_up = (++it & 1023u) == 0u && (wall_ns() - t0 > sync.timeout_ns || ld_flag(sync.err) != 0u);
-                    if (__any_sync(0xffffffffu, give_up)) {
-                        if (lane == 0) atomicExch(sync.err, 1u);
-                        break;
-                    }
-                } while (!__all_sync(0xffffffffu, ok));
-            }
-            __threadfence();  // acquire: the rows read below were written before the counters were published
-            // ping-pong: pass p reads what pass p-1 wrote
-            const float* in = ((pass & 1) ? fld.next : fld.alt) + jsafe;
-            float* out = ((pass & 1) ? fld.alt : fld.next) + jsafe;
-            cx.prev = in;
-            cx.next = out;
-            asm volatile("" : "+l"(cx.prev), "+l"(cx.next));
-        }
-
-        float4 W[T][3];
-        float4 RH[NRH];
-        float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
-        float wl[T], er[T];
-        float4 UV[2][3];
-        float4 XG[3][3];
+    float4 W[T][3];
+    float4 RH[NRH];
+    float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
+    float wl[T], er[T];
+    float4 UV[2][3];
+    float4 XG[3][3];
 #pragma unroll
-        for (int m = 0; m < 3; ++m) UV[0][m] = UV[1][m] = XG[0][m] = XG[1][m] = XG[2][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < 3; ++m) UV[0][m] = UV[1][m] = XG[0][m] = XG[1][m] = XG[2][m] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int s = 0; s < T; ++s) {
-            wl[s] = er[s] = 0.f;
+    for (int s = 0; s < T; ++s) {
+        wl[s] = er[s] = 0.f;
 #pragma unroll
-            for (int m = 0; m < 3; ++m) W[s][m] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int m = 0; m < NRH; ++m) RH[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-        // ---- prologue: rows rs .. rs+PFD-1 in flight
-        constexpr bool RHS_LANDS_MIRRORED = !RHS_REGS && PIN_ZERO < 2;
-#pragma unroll
-        for (int p = 0; p < kPFD; ++p) {
-            const int rl = cx.rs + p;
-            if (rl <= cx.re) {
-                const size_t off = (size_t)rl * cx.pitch;
-                if (PIN_ZERO != 1) cp_async16_s(slot8(cx.sp, rl), cx.prev + off, cx.cp_bytes);
-                if (RHS_LANDS_MIRRORED) {
-                    const unsigned w = slot_wr(cx.sr, rl);
-                    cp_async16_s(w, cx.rhs + off, cx.cp_bytes);
-                    if (mirrored(rl)) cp_async16_s(w + (kRingR << 9), cx.rhs + off, cx.cp_bytes);
-                } else {
-                    cp_async16_s(slot8(cx.sr, rl), cx.rhs + off, cx.cp_bytes);
-                }
-            }
-            cp_async_commit();
-        }
-        Run st;
-        st.off_in = (cx.rs + kPFD) * cx.pitch;
-        st.off_out = (cx.rs - T) * cx.pitch;
-
-        if (!cx.edge_warp)
-            march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
-        else
-            march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
-        cp_async_wait<0>();
-
-        if (CHAIN && npasses > 1) {
-            // publish: this warp's rows of pass `pass` are visible device-wide before the counter moves
-            __threadfence();
-            __syncwarp();
-            if (lane == 0) st_flag(sync.flags + (size_t)blockIdx.y * sync.stride + gw, ld_flag(sync.ctl + SY_GEN) + (unsigned)pass + 1u);
-        }
+        for (int m = 0; m < 3; ++m) W[s][m] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (CHAIN && npasses > 1 && lane == 0) {
-        // the last warp out advances the generation for the next launch that uses this sync block
-        const unsigned gen = ld_flag(sync.ctl + SY_GEN);
-        __threadfence();
-        if (atomicAdd(sync.ctl + SY_DONE, 1u) == sync.total - 1u) {
-            st_flag(sync.ctl + SY_DONE, 0u);
-            st_flag(sync.ctl + SY_GEN, gen + (unsigned)npasses);
+#pragma unroll
+    for (int m = 0; m < NRH; ++m) RH[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    // ---- prologue: rows rs .. rs+PFD-1 in flight
+    constexpr bool RHS_LANDS_MIRRORED = !RHS_REGS && PIN_ZERO < 2;
+#pragma unroll
+    for (int p = 0; p < kPFD; ++p) {
+        const int rl = cx.rs + p;
+        if (rl <= cx.re) {
+            const size_t off = (size_t)rl * cx.pitch;
+            if (PIN_ZERO != 1) cp_async16_s(slot8(cx.sp, rl), cx.prev + off, cx.cp_bytes);
+            if (RHS_LANDS_MIRRORED) {
+                const unsigned w = slot_wr(cx.sr, rl);
+                cp_async16_s(w, cx.rhs + off, cx.cp_bytes);
+                if (mirrored(rl)) cp_async16_s(w + (kRingR << 9), cx.rhs + off, cx.cp_bytes);
+            } else {
+                cp_async16_s(slot8(cx.sr, rl), cx.rhs + off, cx.cp_bytes);
+            }
         }
+        cp_async_commit();
     }
+    Run st;
+    st.off_in = (cx.rs + kPFD) * cx.pitch;
+    st.off_out = (cx.rs - T) * cx.pitch;
+
+    if (!cx.edge_warp)
+        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
+    else
+        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
+    cp_async_wait<0>();
 }
 
 // Host-side planner.  One wave, every resident warp slot busy, all warps finishing together:
@@ -721,8 +624,7 @@ inline ClassPlan plan_class(int rows, int T, int RS, double cost_budget, double 
 }
 
 template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, int MINB>
-cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, int sm_count, cudaStream_t st, int npasses,
-                       const StreamChain& chain) {
+cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& tune, int sm_count, cudaStream_t st) {
     auto kern = k_jacobi_stream<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, MINB>;
     constexpr int RS = RHS_REGS ? rs_of(T) : 3;
     int wpc = tune.warps_per_cta > 0 ? tune.warps_per_cta : 4;
@@ -786,40 +688,26 @@ cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& t
     plan.warps_int = n_int * ci.chunks;
     const long total_warps = (long)plan.warps_int + (long)plan.n_edge_strips * ce.chunks;
     dim3 grid((unsigned)((total_warps + wpc - 1) / wpc), b.n);
-    StreamSync sync = {nullptr, nullptr, nullptr, 1, 0u, 0u, 0ull};
-    if (npasses > 1) {
-        // chained passes: every warp of the launch must be resident at once (one wave) and needs a progress counter
-        if (PIN_ZERO != 0 || chain.block == nullptr || chain.err == nullptr) return cudaErrorInvalidValue;
-        if ((long)grid.x * b.n > (long)occ_cache[wpc] * sm_count) return cudaErrorCooperativeLaunchTooLarge;
-        if ((size_t)total_warps * b.n + kChainCtlWords > chain.words) return cudaErrorInvalidValue;
-        sync.ctl = chain.block;
-        sync.err = chain.err;
-        sync.flags = chain.block + kChainCtlWords;
-        sync.npasses = npasses;
-        sync.stride = (unsigned)total_warps;
-        sync.total = (unsigned)(total_warps * b.n);
-        sync.timeout_ns = chain.timeout_ns;
-    }
-    kern<<<grid, wpc * 32, smem, st>>>(g, b, plan, sync);
+    kern<<<grid, wpc * 32, smem, st>>>(g, b, plan);
     return cudaGetLastError();
 }
 
 template <int T, bool RHS_REGS, int MINB>
 cudaError_t launch_T(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, const StreamTuning& tune, int sm_count,
-                     cudaStream_t st, int npasses, const StreamChain& chain) {
+                     cudaStream_t st) {
     if (!diffuse) {
         if (b.f[0].aux != nullptr)  // first pressure pass with the divergence fused in: prev = u, rhs = v
-            return launch_one<T, false, F2D_DIV_F64, 2, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
-        if (b.f[0].prev == nullptr) return launch_one<T, false, F2D_DIV_F64, 1, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
-        return launch_one<T, false, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
+            return launch_one<T, false, F2D_DIV_F64, 2, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        if (b.f[0].prev == nullptr) return launch_one<T, false, F2D_DIV_F64, 1, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        return launch_one<T, false, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     }
     if (divmode == F2D_DIV_F64) {
         if (b.f[0].aux != nullptr)  // first diffuse pass with add_sources fused in: prev = field, rhs = source
-            return launch_one<T, true, F2D_DIV_F64, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
-        return launch_one<T, true, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
+            return launch_one<T, true, F2D_DIV_F64, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+        return launch_one<T, true, F2D_DIV_F64, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
     }
-    if (b.f[0].aux != nullptr) return launch_one<T, true, F2D_DIV_F32_CORR, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
-    return launch_one<T, true, F2D_DIV_F32_CORR, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st, npasses, chain);
+    if (b.f[0].aux != nullptr) return launch_one<T, true, F2D_DIV_F32_CORR, 3, RHS_REGS, MINB>(g, b, tune, sm_count, st);
+    return launch_one<T, true, F2D_DIV_F32_CORR, 0, RHS_REGS, MINB>(g, b, tune, sm_count, st);
 }
 
 }  // namespace
@@ -829,18 +717,17 @@ bool stream_supported(const Geom& g, int T) {
     return g.cols >= 4 && (g.cols % 4 == 0) && (g.pitch % 4 == 0) && g.rows >= 3;
 }
 
-cudaError_t launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int npasses,
-                                 const StreamTuning& tune, int sm_count, cudaStream_t st, const StreamChain& chain) {
-    // npasses passes of T sweeps each in one launch (the step driver decomposes K into passes of 8/4/2/1 sweeps);
-    // npasses > 1 needs a plain pass (no fused first pass), b.f[i].alt and a sync block
+cudaError_t launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
+                                 const StreamTuning& tune, int sm_count, cudaStream_t st) {
+    (void)sweeps;  // == T: the step driver decomposes K into passes of 8/4/2/1 sweeps
     // T = 8 keeps the right-hand side in the smem ring (unroll 3): with a register ring the unrolled
     // row loop (9 x 8 levels) outgrows the instruction cache.  MINB = resident 128-thread CTAs per SM the register
     // allocator must allow: T = 8 -> 3 (168 regs), T = 4 -> 4 (128 regs).
     switch (T) {
-        case 1: return launch_T<1, true, 6>(g, b, diffuse, divmode, tune, sm_count, st, npasses, chain);
-        case 2: return launch_T<2, true, 6>(g, b, diffuse, divmode, tune, sm_count, st, npasses, chain);
-        case 4: return launch_T<4, true, 4>(g, b, diffuse, divmode, tune, sm_count, st, npasses, chain);
-        default: return launch_T<8, false, 3>(g, b, diffuse, divmode, tune, sm_count, st, npasses, chain);
+        case 1: return launch_T<1, true, 6>(g, b, diffuse, divmode, tune, sm_count, st);
+        case 2: return launch_T<2, true, 6>(g, b, diffuse, divmode, tune, sm_count, st);
+        case 4: return launch_T<4, true, 4>(g, b, diffuse, divmode, tune, sm_count, st);
+        default: return launch_T<8, false, 3>(g, b, diffuse, divmode, tune, sm_count, st);
     }
 }
 

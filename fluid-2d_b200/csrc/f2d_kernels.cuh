@@ -11,8 +11,6 @@ struct RelaxField {
     const float* prev;  // iterate k   (nullptr: identically zero -- first pressure pass)
     const float* rhs;   // x0 (diffuse) or divergence (pressure)
     float* next;        // iterate k + sweeps
-    float* alt;         // chained passes (npasses > 1): the second ping-pong buffer -- pass 0 writes next, pass 1 reads next
-                        // and writes alt, pass 2 reads alt and writes next, ...  (may alias prev)
     float* aux;         // fused first passes, else nullptr.  pressure: prev = u, rhs = v, aux = divergence out;
                         // diffuse: prev = field, rhs = source, aux = x0 out (the field after add_sources)
     int kind;           // F2D_BND_*
@@ -112,22 +110,10 @@ struct StreamTuning {
     int min_chunk_mult; // chunks own at least min_chunk_mult * T rows (0 = 2)
     int edge_cost_pct;  // cost of an edge strip's row step in percent of an interior strip's (0 = default)
 };
-// Sync block of a launch that chains several passes (f2d_jacobi_stream.cu, StreamSync): kChainCtlWords control words
-// followed by one progress counter per warp.  Zeroed once at allocation; launches that share a block must be ordered
-// (same stream or graph dependency).
-constexpr size_t kChainCtlWords = 16;
-constexpr size_t kChainBlockWords = 4096;  // >= kChainCtlWords + resident warps of one launch (6 CTAs x 4 warps x 148 SMs = 3552)
-struct StreamChain {
-    unsigned* block;  // nullptr: single-pass launches only
-    size_t words;
-    unsigned* err;    // device word raised when a wait timed out
-    unsigned long long timeout_ns;
-};
-// returns false if (T, geometry) is not supported by the streaming kernel.
+// `sweeps` (1..T) Jacobi sweeps in one pass over the field(s); returns false if (T, geometry)
+// is not supported by the streaming kernel.
 bool stream_supported(const Geom& g, int T);
-// `npasses` passes of T Jacobi sweeps each over the field(s) in one launch; the result of the last pass is in
-// (npasses & 1) ? next : alt
-cudaError_t launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int npasses,
-                                 const StreamTuning& tune, int sm_count, cudaStream_t st, const StreamChain& chain);
+cudaError_t launch_jacobi_stream(const Geom& g, const RelaxBatch& b, bool diffuse, int divmode, int T, int sweeps,
+                                 const StreamTuning& tune, int sm_count, cudaStream_t st);
 
 }  // namespace f2d

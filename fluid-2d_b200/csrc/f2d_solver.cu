@@ -96,22 +96,6 @@ struct f2d_solver {
     uint64_t graph_kernels = 0;  // kernel launches inside one replay of the graph
     uint64_t launches = 0;       // kernel launches issued so far (graph nodes included)
     StreamTuning tune = {0, 0, 0, 0, 0, 0};
-    // chained relaxation passes (f2d_jacobi_stream.cu: several passes per launch, neighbour-to-neighbour progress
-    // counters).  Every launch takes the next sync block of a ring, so the kernel nodes of one captured graph (which may
-    // run concurrently in the solve() pipeline) never share one; F2D_STREAM_CHAIN=0 launches one pass per kernel.
-    static constexpr int kChainBlocks = 64;
-    unsigned* chain_mem = nullptr;  // kChainBlocks * kChainBlockWords words + 1 error word
-    int chain_next = 0;
-    bool chain_passes = true;
-    StreamChain next_chain() {
-        StreamChain c;
-        c.block = chain_mem ? chain_mem + (size_t)chain_next * kChainBlockWords : nullptr;
-        c.words = kChainBlockWords;
-        c.err = chain_mem ? chain_mem + (size_t)kChainBlocks * kChainBlockWords : nullptr;
-        c.timeout_ns = p2p_timeout_ns;
-        chain_next = (chain_next + 1) % kChainBlocks;
-        return c;
-    }
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // solve(): the density field is final long before the velocity projections finish; it is copied
@@ -167,9 +151,9 @@ struct f2d_solver {
         float t = dt * (float)global_cells();  // src/fluid_solver_gpu.cu:79, left to right in fp32
         k.a = t * rate;
         k.c = 1.0 + 4.0 * (double)k.a;  // gpu.cu:82
-        k.rc = (float)(1.0 / k.c);
-        k.ch = (float)k.c;
-        k.cl = (float)(k.c - (double)k.ch);
+        const double r = 1.0 / k.c;
+        k.rc = (float)r;
+        k.rl = (float)(r - (double)k.rc);
         return k;
     }
     float dt0(float dt) const { return (float)(std::sqrt((double)global_cells()) * (double)dt); }  // gpu.cu:334
@@ -319,22 +303,6 @@ struct f2d_solver {
                 }
                 if (m) F2D_TRY(exchange(todo, m));
             }
-            // passes chained into this launch: all remaining passes of this T on one GPU; on slabs as many as the halo
-            // still covers (inv grows by T per pass); the fused first pass (add_sources) is a launch of its own
-            int np = 1;
-            bool zero_start = false;  // a pass that starts from p == 0 is a kernel variant of its own, too
-            for (int i = 0; i < n; ++i) zero_start |= (cur[i] == nullptr);
-            if (stream_mode && chain_passes && chain_mem && !fuse_src && !zero_start) {
-                np = (int)(left / T);
-                if (multi()) {
-                    for (int i = 0; i < n; ++i) {
-                        const int ip = cur[i] ? get_inv(cur[i]) : 0;
-                        np = std::min(np, (H() - ip) / (int)T);
-                        np = std::min(np, (H() + 1 - get_inv(rhs[i])) / (int)T);
-                    }
-                    np = std::max(np, 1);
-                }
-            }
             RelaxBatch b;
             b.n = n;
             b.dt = src_dt;
@@ -342,29 +310,25 @@ struct f2d_solver {
                 b.f[i].prev = cur[i];
                 b.f[i].rhs = fuse_src ? src[i] : rhs[i];
                 b.f[i].next = flip ? pong[i] : ping[i];
-                b.f[i].alt = flip ? ping[i] : pong[i];
                 b.f[i].aux = fuse_src ? const_cast<float*>(rhs[i]) : nullptr;
                 b.f[i].kind = kinds[i];
-                b.f[i].coef = coefs ? coefs[i] : DiffuseCoef{0.f, 0.f, 0.f, 0.f, 1.0};
+                b.f[i].coef = coefs ? coefs[i] : DiffuseCoef{0.f, 0.f, 0.f, 1.0};
             }
             if (stream_mode) {
-                const StreamChain chain = (np > 1) ? next_chain() : StreamChain{nullptr, 0, nullptr, 0ull};
-                const cudaError_t le = launch_jacobi_stream(g, b, diffuse, (int)cfg.divide_mode, (int)T, np, tune, sm_count, stream, chain);
-                if (le != cudaSuccess) return fail(F2D_ERR_CUDA, "streaming Jacobi launch (%d passes of T=%u) failed: %s", np, T, cudaGetErrorString(le));
+                const cudaError_t le = launch_jacobi_stream(g, b, diffuse, (int)cfg.divide_mode, (int)T, (int)T, tune, sm_count, stream);
+                if (le != cudaSuccess) return fail(F2D_ERR_CUDA, "streaming Jacobi pass (T=%u) could not be launched: %s", T, cudaGetErrorString(le));
             } else
                 launch_jacobi_naive(g, b, diffuse, (int)cfg.divide_mode, stream);
             count();
             for (int i = 0; i < n; ++i) {
                 const int ip = cur[i] ? get_inv(cur[i]) : 0;
                 if (fuse_src) set_inv(rhs[i], ip);  // x0 is pointwise in the field
-                const int inv_out = std::max(ip + (int)T * np, get_inv(rhs[i]) + (int)T * np - 1);
-                set_inv(b.f[i].next, inv_out);
-                if (np > 1) set_inv(b.f[i].alt, inv_out);
-                cur[i] = (np & 1) ? b.f[i].next : b.f[i].alt;
+                set_inv(b.f[i].next, std::max(ip + (int)T, get_inv(rhs[i]) + (int)T - 1));
+                cur[i] = b.f[i].next;
             }
             fuse_src = false;
-            flip ^= (np & 1);
-            left -= T * (uint32_t)np;
+            flip ^= 1;
+            left -= T;
         }
         for (int i = 0; i < n; ++i) {
             out[i] = cur[i];
@@ -402,11 +366,10 @@ struct f2d_solver {
             b.f[0].prev = u_in;
             b.f[0].rhs = v_in;
             b.f[0].next = p1;
-            b.f[0].alt = nullptr;
             b.f[0].aux = dv;
             b.f[0].kind = F2D_BND_CONTINUOUS;
-            b.f[0].coef = DiffuseCoef{-0.5f * h(), 0.f, 0.f, 0.f, 1.0};
-            const cudaError_t le = launch_jacobi_stream(g, b, false, (int)cfg.divide_mode, (int)T, 1, tune, sm_count, stream, StreamChain{nullptr, 0, nullptr, 0ull});
+            b.f[0].coef = DiffuseCoef{-0.5f * h(), 0.f, 0.f, 1.0};
+            const cudaError_t le = launch_jacobi_stream(g, b, false, (int)cfg.divide_mode, (int)T, (int)T, tune, sm_count, stream);
             if (le != cudaSuccess) return fail(F2D_ERR_CUDA, "fused divergence + pressure pass (T=%u) could not be launched: %s", T, cudaGetErrorString(le));
             count();
             const int iuv = std::max(get_inv(u_in), get_inv(v_in));
@@ -1423,13 +1386,6 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
         return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
     cudaMemsetAsync(s->oob_flag, 0, sizeof(int), s->stream);
     s->host_register = env_int("F2D_HOST_REGISTER", 0) != 0;
-    s->chain_passes = env_int("F2D_STREAM_CHAIN", 1) != 0;
-    if (s->cfg.jacobi_mode == F2D_JACOBI_STREAM && s->chain_passes) {
-        const size_t words = (size_t)f2d_solver::kChainBlocks * kChainBlockWords + 16;
-        if (cudaMalloc(&s->chain_mem, words * sizeof(unsigned)) != cudaSuccess)
-            return cleanup(fail(F2D_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError())));
-        cudaMemsetAsync(s->chain_mem, 0, words * sizeof(unsigned), s->stream);
-    }
     if (s->cpu_sem()) {
         const uint32_t k = std::max(3u * s->cfg.diffuse_iters, s->cfg.project_iters);
         s->gs_flag_cap = gs_flag_words(s->g.rows, 1, (int)std::max(k, 1u));
@@ -1479,7 +1435,6 @@ F2D_API void f2d_destroy(f2d_solver* s) {
         s->state[i] = nullptr;
     if (s->arena) cudaFree(s->arena);
     if (s->oob_flag) cudaFree(s->oob_flag);
-    if (s->chain_mem) cudaFree(s->chain_mem);
     if (s->render_buf) cudaFree(s->render_buf);
     if (s->gs_flags) cudaFree(s->gs_flags);
     if (s->gs_aux) cudaFree(s->gs_aux);
@@ -1621,16 +1576,6 @@ F2D_API int f2d_sync(f2d_solver* s) {
         if (err) {
             cudaMemset(s->flags + 2, 0, sizeof(unsigned));  // report once; later exchanges wait normally again
             return fail(F2D_ERR_STATE, "halo exchange timed out waiting for a neighbour GPU (state invalid since then)");
-        }
-    }
-    if (s->chain_mem) {
-        unsigned err = 0;
-        unsigned* word = s->chain_mem + (size_t)f2d_solver::kChainBlocks * kChainBlockWords;
-        F2D_CUDA(cudaMemcpy(&err, word, sizeof(unsigned), cudaMemcpyDeviceToHost));
-        if (err) {
-            // the counters of the launch that gave up are inconsistent: start all sync blocks afresh
-            cudaMemset(s->chain_mem, 0, ((size_t)f2d_solver::kChainBlocks * kChainBlockWords + 16) * sizeof(unsigned));
-            return fail(F2D_ERR_STATE, "chained Jacobi passes: a warp waited for its neighbours for too long (results invalid)");
         }
     }
     if (s->gs_aux) {

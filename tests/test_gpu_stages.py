@@ -66,8 +66,8 @@ def test_diffuse_fp32_corrected_divide_within_1ulp(f2d, sfo, gpu_ok, mode, T):
 @pytest.mark.parametrize("a", [1.7e5, 2.7e6, 1.07e7, 4.3e7])
 def test_diffuse_fp32_corrected_divide_at_the_published_coefficients(f2d, sfo, gpu_ok, mode, T, a):
     """The diffusion coefficient a = dt * N^2 * rate of the configurations the numbers are published for:
-    1.7e5 (4096^2), 2.7e6 (16384^2), 1.07e7 (32768^2; c = 1 + 4a no longer fits 24 bits, so the ch + cl split of
-    the divisor matters) and 4.3e7 beyond.  f2d_stage_diffuse takes the rate, so a 256^2 grid reproduces each of
+    1.7e5 (4096^2), 2.7e6 (16384^2), 1.07e7 (32768^2; c = 1 + 4a no longer fits 24 bits; the rc + rl split of the
+    reciprocal carries 48) and 4.3e7 beyond.  f2d_stage_diffuse takes the rate, so a 256^2 grid reproduces each of
     them.  Against the reference's fp64 divide after 20 sweeps: <= 2 ulp per cell, rel-L2 <= 1e-7, at most 1 cell
     in 10^4 different at all."""
     n = 256
