@@ -54,7 +54,11 @@
 //   * Also built, measured and dropped in round 2 (git history; numbers in profiles/ab_r02_*.log): (a) the passes of one
 //     relaxation chained inside ONE launch, each warp waiting only for the progress counters of its 3 x 3 neighbouring
 //     (strip, chunk) warps: the device-scope fence + counter round trip per pass costs as much as the launch it replaces
-//     inside a CUDA graph (4096^2 step 3.44 vs 3.37 ms, 256^2 0.148 vs 0.109 ms); (b) F2D_RHS_GEN=1, below.
+//     inside a CUDA graph (4096^2 step 3.44 vs 3.37 ms, 256^2 0.148 vs 0.109 ms); (b) "rhs generations": each rhs row read
+//     back from shared memory once per three levels and kept in registers for the two following steps (3 or 4 instead of
+//     8 LDS.128 per row step): shared-memory wavefronts fall from 10.3 M to 6.6 M per pass, but the 24-36 registers that
+//     stay live across steps spill, and with 3 x 70 KB of shared memory per SM the L1 left for local memory is tiny
+//     (long_scoreboard 1.4 cycles per instruction): pressure pass 63-70 us against 53 us.
 #include <algorithm>
 
 #include "f2d_kernels.cuh"
@@ -64,15 +68,11 @@
 #define F2D_SHFL_AHEAD 0  // 1: west/east shuffles issued at the end of the previous row step (costs 2T live
                           // registers; slower since the row step became one basic block, profiles/ab_r01_run7_*.log)
 #endif
-#ifndef F2D_RHS_GEN
-#define F2D_RHS_GEN 0     // rhs in shared memory (T = 8): 1 = each rhs row is read back once per 3 levels and kept in
-                          // registers for the two following steps ("generations"); 0 = one LDS.128 per level and step
-#endif
 #ifndef F2D_PRESSURE_SCALED
 #define F2D_PRESSURE_SCALED 1  // pressure levels carried as 4^s * p (see relax_row): 4 instead of 5 operations per cell-sweep
 #endif
 #ifndef F2D_RHS_MIRROR
-#define F2D_RHS_MIRROR 1  // rhs ring in shared memory: 1 = 16 slots + mirror of slots 0..7 (every row of a step at a
+#define F2D_RHS_MIRROR 0  // rhs ring in shared memory: 1 = 16 slots + mirror of slots 0..7 (every row of a step at a
                           // compile-time offset below one pointer, rows with bit 3 clear are written twice); 0 = plain
                           // 16-slot ring, 8 KB-aligned, one "(row << 9) & mask | base" per read
 #endif
@@ -119,6 +119,11 @@ __device__ __forceinline__ void sts128(unsigned smem_addr, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(smem_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ float4 ld_global_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_global_f4(float* p, const float4& v) {
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -249,7 +254,7 @@ struct Run {
 // EDGE: this warp's strip holds a domain edge column; interior strips are compiled without the edge-column fix.
 template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool FAST, bool EDGE, int RS, int NRH>
 __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int nsteps, float4 (&W)[T][3], float4 (&RH)[NRH],
-                                          float4& out_prev, float (&wl)[T], float (&er)[T], float4 (&UV)[2][3], float4 (&XG)[3][3]) {
+                                          float (&wl)[T], float (&er)[T], float4 (&UV)[2][3]) {
     static_assert(T <= kMirror, "the mirrored ring covers T <= 8 rows");
     // PIN_ZERO == 2: the first pressure pass with the divergence fused in (gpu.cu:164-177 + :376): the two
     // async rings carry u and v rows instead of iterate and rhs; the rhs row r-1 is computed on the fly
@@ -368,16 +373,6 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
         // rhs in shared memory: the rows r-1 .. r-T sit contiguously below this pointer (mirrored ring)
         const unsigned rbase = (FUSE || FSRC) ? cx.sd : cx.sr;
         const unsigned rd = RHS_REGS ? 0u : slot_rd(rbase, r);
-#if F2D_RHS_GEN
-        // Level s reads rhs row r-s-1, which level s-1 read one step earlier: levels are grouped in threes, the first
-        // level of a group loads its row (rows r-1, r-4, r-7) and the row stays in registers for the next two steps,
-        // where the second and third level of the group use it.  3 instead of T shared-memory reads per step; the
-        // generation index has the period of the window registers (3), so it is a compile-time constant.
-        if (!RHS_REGS) {
-#pragma unroll
-            for (int gq = 0; 3 * gq < T; ++gq) XG[gq][m3(k)] = lds128(slot_back(rbase, rd, r, 3 * gq + 1));
-        }
-#endif
 #pragma unroll
         for (int s = 0; s < T; ++s) {
             const int q = r - s - 1;
@@ -390,11 +385,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                 if (RHS_REGS)
                     rhs = RH[mrs(k - s - 1, RS)];
                 else
-#if F2D_RHS_GEN
-                    rhs = XG[s / 3][m3(k - s % 3)];
-#else
                     rhs = lds128(slot_back(rbase, rd, r, s + 1));
-#endif
                 float4 nw = relax_row<DIFFUSE, DIVMODE, T>(a, b, c, l, rt, rhs, cx.coef, s);
                 // interior rows of an edge strip: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32), as
                 // two predicated selects (no branch) so that a whole row step stays one basic block
@@ -405,7 +396,6 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                 if (s + 1 < T) {
                     W[sn][sm] = nw;
                 } else {
-                    out_prev = nw;
                     if (cx.own_x && q >= cx.y0 && q < cx.y1) st_global_f4(cx.next + st.off_out, nw);
                 }
                 if (!FAST && s == s_top) {  // global top edge row of the same level (corners kept)
@@ -416,7 +406,9 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                         st_global_f4(cx.next, e);
                 }
             } else if (!FAST && s == s_bot && q >= cx.rs + 1) {  // global bottom edge row
-                const float4 inner = (s + 1 < T) ? W[sn][sa] : out_prev;
+                // the adjacent interior row of the last level was stored one step ago by this very lane (the bottom chunk
+                // owns it): read it back instead of keeping every output row alive in registers for this one step
+                const float4 inner = (s + 1 < T) ? W[sn][sa] : ld_global_f4(cx.next + (st.off_out - cx.pitch));
                 const float4 e = edge_row(inner, W[s][sm], corner_carry<DIFFUSE, T>(s), cx.neg_r, hl, hr);
                 if (s + 1 < T)
                     W[sn][sm] = e;
@@ -442,15 +434,15 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
 // all row steps of one warp; EDGE is the warp's class (chosen once, outside the row loop)
 template <int T, bool DIFFUSE, int DIVMODE, int PIN_ZERO, bool RHS_REGS, bool EDGE, int RS, int NRH>
 __device__ __forceinline__ void march(const Ctx& cx, Run& st, int nsteps, int top_lo, int top_hi, int bot_lo, int bot_hi,
-                                      float4 (&W)[T][3], float4 (&RH)[NRH], float4& out_prev, float (&wl)[T], float (&er)[T],
-                                      float4 (&UV)[2][3], float4 (&XG)[3][3]) {
+                                      float4 (&W)[T][3], float4 (&RH)[NRH], float (&wl)[T], float (&er)[T],
+                                      float4 (&UV)[2][3]) {
     for (int rb = 0; rb < nsteps; rb += RS) {
         const int r_first = cx.rs + rb, r_last = r_first + RS - 1;
         const bool edge_block = (r_first <= top_hi && r_last >= top_lo) || (r_first <= bot_hi && r_last >= bot_lo);
         if (!edge_block)
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, out_prev, wl, er, UV, XG);
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, wl, er, UV);
         else
-            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, out_prev, wl, er, UV, XG);
+            run_block<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, EDGE, RS, NRH>(cx, st, rb, nsteps, W, RH, wl, er, UV);
     }
 }
 
@@ -528,6 +520,10 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     // the first / last chunk are `edge_trim` rows shorter: their edge-rule steps cost more
     cx.y0 = (chunk == 0) ? 0 : chunk * chunk_rows - edge_trim;
     cx.y1 = (chunk == n_chunks - 1) ? g.rows : (chunk + 1) * chunk_rows - edge_trim;
+    // the chunk that owns the bottom edge row also owns the interior row above it: the edge rule of the last level reads
+    // that row back from what this warp stored one step earlier (run_block)
+    if (chunk == n_chunks - 1 && chunk > 0) cx.y0 = min(cx.y0, g.rows - 2);
+    if (chunk == n_chunks - 2) cx.y1 = min(cx.y1, g.rows - 2);
     // T warm-up rows above the first owned row; a chunk that owns only the global bottom edge row
     // must warm up for row rows-2, which the edge rule copies from
     cx.rs = max(0, min(cx.y0, g.rows - 2) - T);
@@ -547,12 +543,10 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
 
     float4 W[T][3];
     float4 RH[NRH];
-    float4 out_prev = make_float4(0.f, 0.f, 0.f, 0.f);
     float wl[T], er[T];
     float4 UV[2][3];
-    float4 XG[3][3];
 #pragma unroll
-    for (int m = 0; m < 3; ++m) UV[0][m] = UV[1][m] = XG[0][m] = XG[1][m] = XG[2][m] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int m = 0; m < 3; ++m) UV[0][m] = UV[1][m] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int s = 0; s < T; ++s) {
         wl[s] = er[s] = 0.f;
@@ -562,6 +556,11 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
 #pragma unroll
     for (int m = 0; m < NRH; ++m) RH[m] = make_float4(0.f, 0.f, 0.f, 0.f);
 
+    // programmatic dependent launch (StreamTuning::pdl): everything above ran while the previous kernel of the stream was
+    // still draining; its results (and the buffers it read, which this pass overwrites) are safe to touch from here on.
+    // The next pass may be scheduled as soon as CTAs of this one retire.  Both are no-ops in a normal launch.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // ---- prologue: rows rs .. rs+PFD-1 in flight
     constexpr bool RHS_LANDS_MIRRORED = !RHS_REGS && PIN_ZERO < 2;
 #pragma unroll
@@ -585,9 +584,9 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     st.off_out = (cx.rs - T) * cx.pitch;
 
     if (!cx.edge_warp)
-        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
+        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, wl, er, UV);
     else
-        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, out_prev, wl, er, UV, XG);
+        march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, true, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, wl, er, UV);
     cp_async_wait<0>();
 }
 
@@ -688,6 +687,19 @@ cudaError_t launch_one(const Geom& g, const RelaxBatch& b, const StreamTuning& t
     plan.warps_int = n_int * ci.chunks;
     const long total_warps = (long)plan.warps_int + (long)plan.n_edge_strips * ce.chunks;
     dim3 grid((unsigned)((total_warps + wpc - 1) / wpc), b.n);
+    if (tune.pdl) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = grid;
+        lc.blockDim = dim3(wpc * 32);
+        lc.dynamicSmemBytes = smem;
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        return cudaLaunchKernelEx(&lc, kern, g, b, plan);
+    }
     kern<<<grid, wpc * 32, smem, st>>>(g, b, plan);
     return cudaGetLastError();
 }

@@ -105,7 +105,8 @@ void launch_velocity_to_lines(const Geom& g, const float* u, const float* v, voi
 struct StreamTuning {
     int chunk_rows;     // output rows per warp (0 = auto)
     int warps_per_cta;  // 0 = auto
-    int rhs_in_smem;    // unused since round 2 (T <= 4: register ring, T = 8: smem ring)
+    int pdl;            // 1: programmatic dependent launch -- the pass may be scheduled while its predecessor in the stream
+                        // drains (it waits with griddepcontrol.wait before it touches global memory)
     int min_blocks;     // unused since round 2
     int min_chunk_mult; // chunks own at least min_chunk_mult * T rows (0 = 2)
     int edge_cost_pct;  // cost of an edge strip's row step in percent of an interior strip's (0 = default)

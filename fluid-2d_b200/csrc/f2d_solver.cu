@@ -1346,7 +1346,7 @@ F2D_API int f2d_create(const f2d_config* cfg, f2d_solver** out) {
     }
     s->tune.chunk_rows = env_int("F2D_STREAM_CHUNK_ROWS", 0);
     s->tune.warps_per_cta = env_int("F2D_STREAM_WARPS_PER_CTA", 0);
-    s->tune.rhs_in_smem = env_int("F2D_STREAM_RHS_SMEM", 0);
+    s->tune.pdl = env_int("F2D_STREAM_PDL", 1);
     s->tune.min_blocks = env_int("F2D_STREAM_MIN_BLOCKS", 0);
     s->tune.min_chunk_mult = env_int("F2D_STREAM_MIN_CHUNK_MULT", 0);
     s->tune.edge_cost_pct = env_int("F2D_STREAM_EDGE_COST_PCT", 0);
