@@ -299,9 +299,73 @@ __global__ void __launch_bounds__(kBx* kBy) k_advect_velocity(Geom g, const floa
     v_out[o] = apply_sign(vn, cv.negate);
 }
 
+// float4 version (cols % 4 == 0): one thread = four consecutive cells of one row.  The cells' own velocities (the
+// back-trace) are one 16-byte load per component -- of the adjacent interior row for a global edge row, and the edge
+// columns take their neighbour component of the same float4 (classify_cell's (si, sj)) --, the results two 16-byte
+// stores; the 2 x 4 bilinear taps per cell stay scalar read-only loads (they hit L1/L2 for CFL-bounded steps).
+__global__ void __launch_bounds__(kVx* kVy) k_advect_velocity_v4(Geom g, const float* __restrict__ u0,
+                                                                const float* __restrict__ v0, float* __restrict__ u_out,
+                                                                float* __restrict__ v_out, float dt0, int own_begin, int own_end,
+                                                                int valid_lo, int valid_hi, int* oob_flag) {
+    F2D_ROW_J4();
+    const size_t o = (size_t)i * g.pitch + j;
+    const RowSrc rs = classify_row(g, i);
+    if (rs.keep) {
+        st4(u_out + o, ld4(u0 + o));
+        st4(v_out + o, ld4(v0 + o));
+        return;
+    }
+    const size_t so = (size_t)rs.si * g.pitch + j;
+    const float4 us = ld4(u0 + so), vs = ld4(v0 + so);
+    const float uc[4] = {us.x, us.y, us.z, us.w}, vc[4] = {vs.x, vs.y, vs.z, vs.w};
+    const bool first = (j == 0), last = (j + 3 == g.cols - 1);
+    const bool own = (i >= own_begin && i < own_end);
+    const float ytrace = (float)(g.grow0 + rs.si);
+    float ur[4], vr[4];
+    bool oob = false;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        // source column of cell c: the edge columns evaluate their inward neighbour (gpu.cu:16-17, 31-32)
+        const int cs = (first && c == 0) ? 1 : ((last && c == 3) ? 2 : c);
+        float x = __fmaf_rn(-uc[cs], dt0, (float)(j + cs));
+        float y = __fmaf_rn(-vc[cs], dt0, ytrace);
+        x = fmaxf(1.5f, fminf((float)g.cols - 1.5f, x));
+        y = fmaxf(1.5f, fminf((float)g.grows - 1.5f, y));
+        const Bilinear b = bilinear_setup(x, y);
+        int li0 = b.i0 - g.grow0;
+        oob |= (li0 < valid_lo || li0 + 1 >= valid_hi);
+        li0 = max(0, min(g.rows - 2, li0));
+        const size_t a = (size_t)li0 * g.pitch + b.j0;
+        ur[c] = bilinear_gather(b, __ldg(u0 + a), __ldg(u0 + a + 1), __ldg(u0 + a + g.pitch), __ldg(u0 + a + g.pitch + 1));
+        vr[c] = bilinear_gather(b, __ldg(v0 + a), __ldg(v0 + a + 1), __ldg(v0 + a + g.pitch), __ldg(v0 + a + g.pitch + 1));
+    }
+    if (oob && own) *oob_flag = 1;
+    // signs of the fused boundary pass: u flips in the edge columns, v in the edge rows (gpu.cu:26-54)
+    if (first) ur[0] = -ur[0];
+    if (last) ur[3] = -ur[3];
+    if (rs.edge_row) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) vr[c] = -vr[c];
+        // corners are never written by the reference (gpu.cu:15-23): pass the input through
+        if (first) {
+            ur[0] = u0[o];
+            vr[0] = v0[o];
+        }
+        if (last) {
+            ur[3] = u0[o + 3];
+            vr[3] = v0[o + 3];
+        }
+    }
+    st4(u_out + o, make_float4(ur[0], ur[1], ur[2], ur[3]));
+    st4(v_out + o, make_float4(vr[0], vr[1], vr[2], vr[3]));
+}
+
 void launch_advect_velocity(const Geom& g, const float* u0, const float* v0, float* u_out, float* v_out,
                             float dt0, int own_begin, int own_end, int valid_lo, int valid_hi, int* oob_flag, cudaStream_t st) {
-    k_advect_velocity<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u0, v0, u_out, v_out, dt0, own_begin, own_end, valid_lo, valid_hi, oob_flag);
+    if (g.cols % 4 == 0)
+        k_advect_velocity_v4<<<grid_v4(g), dim3(kVx, kVy), 0, st>>>(g, u0, v0, u_out, v_out, dt0, own_begin, own_end, valid_lo, valid_hi, oob_flag);
+    else
+        k_advect_velocity<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, u0, v0, u_out, v_out, dt0, own_begin, own_end, valid_lo, valid_hi, oob_flag);
 }
 
 // rows [row0, row0 + nrows) of f += src (src is a dense nrows x pitch block): the receiving end of the
@@ -354,6 +418,10 @@ __global__ void __launch_bounds__(kBx* kBy) k_scatter_density(Geom g, const floa
 
 void launch_scatter_density(const Geom& g, const float* src, const float* u, const float* v, float* out,
                             float dt0, int own_begin, int own_end, int* oob_flag, cudaStream_t st) {
+    // one thread per source cell on purpose: the 32 lanes of a warp then hit consecutive addresses with each of the four
+    // RED.ADD (one or two 128-byte lines per instruction).  A float4-per-thread version (three 16-byte loads, 16 REDs per
+    // thread) was measured at 174 us against 96 us at 4096^2: its REDs touch four lines each and the thread serialises 16
+    // of them (lg_throttle 38 cycles per instruction, profiles/ncu_advect_scatter_r02.md)
     k_scatter_density<<<grid2d(g), dim3(kBx, kBy), 0, st>>>(g, src, u, v, out, dt0, own_begin, own_end, oob_flag);
 }
 

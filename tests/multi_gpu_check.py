@@ -145,6 +145,37 @@ def main():
                 good = (not failed_any) and judge(tag, glob, single_gpu(n, kd, kp, T, 1, fields, False), 1, dict(n=n, cells=cells))
                 ok &= good
         dist.barrier()
+    # ---- 4. (F2D_CHECK_BIG=n) a published configuration against the UNMODIFIED reference: n x n canonical fields,
+    #         Kd = Kp = 80, one step on row slabs (fp64 divide), owned rows gathered on rank 0 and compared with
+    #         fluid_solver_gpu's own stage sequence at the same K (oracle/_ref/libref_gpu.so, run live on rank 0's GPU).
+    big = int(os.environ.get("F2D_CHECK_BIG", "0"))
+    if big:
+        from tools import canonical as canon
+
+        n, kd, kp, halo, T = big, 80, 80, 32, 8
+        sl = slabmod.partition(n, world, halo, rank)
+        loc = list(canon.rows(n, sl.row_offset, sl.row_offset + sl.rows))
+        s = make(sl, n, kd, kp, T, True, 0)
+        s.upload(*loc[:3])
+        s.set_sources(*loc[3:])
+        s.step(DIFFUSION_RATE, VISCOSITY, DT, 1)
+        s.sync()
+        out = s.download()
+        s.close()
+        del loc
+        glob = gather_owned(sl, n, halo, out)
+        del out
+        torch.cuda.empty_cache()
+        if rank == 0:
+            from oracle import refs
+
+            if refs.have_gpu():
+                f = list(canon.rows(n, 0, n))
+                ref = refs.ref_gpu().step_k(f[0], f[3], DIFFUSION_RATE, f[1], f[2], f[4], f[5], VISCOSITY, DT, kd, kp, True, 1)[:3]
+                ok &= judge("published_vs_reference_gpu", glob, ref, 1, dict(n=n, kd=kd, kp=kp, halo=halo, T=T))
+            else:
+                report.append(dict(case="published_vs_reference_gpu", skipped="libref_gpu.so did not travel to this box"))
+        dist.barrier()
     if rank == 0:
         print(json.dumps(report, indent=1))
         print("MULTI_GPU_CHECK", "PASS" if ok else "FAIL")
