@@ -64,9 +64,8 @@
 #include "f2d_kernels.cuh"
 
 // A/B switches (tools/build_variants.sh builds one library per combination)
-#ifndef F2D_SHFL_AHEAD
-#define F2D_SHFL_AHEAD 0  // 1: west/east shuffles issued at the end of the previous row step (costs 2T live
-                          // registers; slower since the row step became one basic block, profiles/ab_r01_run7_*.log)
+#ifndef F2D_LEVEL_SPLIT
+#define F2D_LEVEL_SPLIT 1  // T = 8: levels 4..7 run one row behind levels 0..3 (see level_lag)
 #endif
 #ifndef F2D_PRESSURE_SCALED
 #define F2D_PRESSURE_SCALED 1  // pressure levels carried as 4^s * p (see relax_row): 4 instead of 5 operations per cell-sweep
@@ -95,6 +94,17 @@ __host__ __device__ constexpr int mrs(int x, int RS) { return ((x % RS) + RS) % 
 constexpr int kRingR = 16;   // >= PFD + T + 2 for T <= 8
 constexpr int kMirror = 8;   // >= T
 __host__ __device__ constexpr int ring_r_slots(bool rhs_regs) { return rhs_regs ? kRingP : kRingR + (F2D_RHS_MIRROR ? kMirror : 0); }
+
+// Level chain.  Without a lag, level s+1 consumes in the same row step the row level s has just produced: the T levels
+// of a step are ONE dependent chain (FADD -> ... -> next level), and a warp can only overlap the four cells of its
+// float4.  With F2D_LEVEL_SPLIT the upper half of the levels (T = 8: levels 4..7) works one row behind: level 4 reads
+// the row level 3 produced in the PREVIOUS step, so a step consists of two independent chains of four levels that the
+// scheduler interleaves.  Cost: one more drain row per chunk and one more rhs row in the ring; no extra registers
+// across steps (level 3's new row replaces the row level 4 consumed last, in the same window slot).
+__host__ __device__ constexpr int level_split(int T, bool rhs_regs) { return (F2D_LEVEL_SPLIT && T == 8 && !rhs_regs) ? 4 : T; }
+__host__ __device__ constexpr int level_lag(int T, bool rhs_regs, int s) { return s >= level_split(T, rhs_regs) ? 1 : 0; }
+__host__ __device__ constexpr int max_lag(int T, bool rhs_regs) { return level_lag(T, rhs_regs, T - 1); }
+static_assert(kPFD + 8 + max_lag(8, false) + 1 <= kRingR, "rhs ring: rows r + PFD .. r - T - lag");
 
 // Work decomposition.  Warps fall into two classes with different cost per row: class 0 = interior
 // strips, class 1 = the strips that hold a left/right domain edge column (extra edge fix per level).
@@ -264,6 +274,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
     // and written out as the rhs of the later passes
     constexpr bool FSRC = (PIN_ZERO == 3);
     constexpr bool RHS_LANDS_MIRRORED = !RHS_REGS && !FUSE && !FSRC;  // the async copy itself fills the mirrored ring
+    constexpr int SPLIT = level_split(T, RHS_REGS), LAG = max_lag(T, RHS_REGS);  // st.off_out follows row r - T - LAG
     const bool hl = EDGE && cx.has_left, hr = EDGE && cx.has_right;
 #pragma unroll
     for (int k = 0; k < RS; ++k) {
@@ -310,7 +321,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                     sts128(w, x0);
                     if (mirrored(r)) sts128(w + (kRingR << 9), x0);
                 }
-                if (cx.own_x && r >= cx.y0 && r < cx.y1 && r <= cx.re) st_global_f4(cx.aux + (st.off_out + T * cx.pitch), x0);
+                if (cx.own_x && r >= cx.y0 && r < cx.y1 && r <= cx.re) st_global_f4(cx.aux + (st.off_out + (T + LAG) * cx.pitch), x0);
             } else if (!PIN_ZERO)
                 W[0][m3(k)] = lds128(slot8(cx.sp, r));
             else
@@ -345,7 +356,7 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                 if (mirrored(qd)) sts128(w + (kRingR << 9), dv);
             }
             if (cx.own_x && qd >= cx.rs + 1 && qd <= cx.re - 1) {
-                if (qd >= cx.y0 && qd < cx.y1) st_global_f4(cx.aux + (st.off_out + (T - 1) * cx.pitch), dv);
+                if (qd >= cx.y0 && qd < cx.y1) st_global_f4(cx.aux + (st.off_out + (T + LAG - 1) * cx.pitch), dv);
                 // the edge rows of the stored field copy the adjacent interior row, corners are the memset zeros
                 float4 e = dv;
                 e.x = hl ? 0.f : e.x;
@@ -354,38 +365,35 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                 if (qd == cx.re - 1 && cx.bot_dom) st_global_f4(cx.aux + (size_t)cx.re * cx.pitch, e);
             }
         }
-#if !F2D_SHFL_AHEAD
-        // west/east neighbours of the centre rows of all levels (rows produced in the previous step)
+        // west/east neighbours of the centre rows of all levels (rows produced in earlier steps)
 #pragma unroll
         for (int s = 0; s < T; ++s) {
-            const float4 bb = W[s][m3(k - s - 1)];
+            const float4 bb = W[s][m3(k - s - 1 - level_lag(T, RHS_REGS, s))];
             wl[s] = __shfl_up_sync(0xffffffffu, bb.w, 1);
             er[s] = __shfl_down_sync(0xffffffffu, bb.x, 1);
         }
-#endif
 
-        // 3. level s+1 produces row q = r - s - 1 from level s rows q-1, q, q+1; wl[s], er[s] are the
-        //    west/east neighbours of the centre row (a row produced in the previous step).
-        //    active levels: rs+1 <= q <= re-1  <=>  s_lo <= s <= s_hi
-        const int s_lo = r - cx.re, s_hi = r - cx.rs - 2;
-        const int s_top = cx.top_dom ? r - 2 : -1;           // level whose q == 1 (global top edge above it)
-        const int s_bot = cx.bot_dom ? r - cx.re - 1 : -1;   // level whose q == re == global bottom edge row
-        // rhs in shared memory: the rows r-1 .. r-T sit contiguously below this pointer (mirrored ring)
+        // 3. level s+1 produces row q = r - s - 1 - lag(s) from level s rows q-1, q, q+1; wl[s], er[s] are the
+        //    west/east neighbours of the centre row.  A level is active while rs+1 <= q <= re-1.
+        //    The lagging levels go FIRST in program order: level SPLIT still reads the window slot that level SPLIT-1
+        //    overwrites in this step (rows q-1 of the one and q of the other share a slot).
         const unsigned rbase = (FUSE || FSRC) ? cx.sd : cx.sr;
         const unsigned rd = RHS_REGS ? 0u : slot_rd(rbase, r);
 #pragma unroll
-        for (int s = 0; s < T; ++s) {
-            const int q = r - s - 1;
-            const int sa = m3(k - s - 2), sm = m3(k - s - 1), sc = m3(k - s);
+        for (int si = 0; si < T; ++si) {
+            const int s = (si < T - SPLIT) ? SPLIT + si : si - (T - SPLIT);
+            const int lag = level_lag(T, RHS_REGS, s);
+            const int q = r - s - 1 - lag;
+            const int sa = m3(k - s - 2 - lag), sm = m3(k - s - 1 - lag), sc = m3(k - s - lag);
             const int sn = (s + 1 < T) ? s + 1 : 0;  // keeps the dead branch's index in range
-            if (FAST || (s >= s_lo && s <= s_hi)) {
+            if (FAST || (q >= cx.rs + 1 && q <= cx.re - 1)) {
                 const float4 a = W[s][sa], b = W[s][sm], c = W[s][sc];
                 const float l = wl[s], rt = er[s];
                 float4 rhs;
                 if (RHS_REGS)
                     rhs = RH[mrs(k - s - 1, RS)];
                 else
-                    rhs = lds128(slot_back(rbase, rd, r, s + 1));
+                    rhs = lds128(slot_back(rbase, rd, r, s + 1 + lag));
                 float4 nw = relax_row<DIFFUSE, DIVMODE, T>(a, b, c, l, rt, rhs, cx.coef, s);
                 // interior rows of an edge strip: col 0 = +/- col 1, col N-1 = +/- col N-2 (gpu.cu:16-17, 31-32), as
                 // two predicated selects (no branch) so that a whole row step stays one basic block
@@ -398,14 +406,14 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                 } else {
                     if (cx.own_x && q >= cx.y0 && q < cx.y1) st_global_f4(cx.next + st.off_out, nw);
                 }
-                if (!FAST && s == s_top) {  // global top edge row of the same level (corners kept)
+                if (!FAST && cx.top_dom && q == 1) {  // global top edge row of the same level (corners kept)
                     const float4 e = edge_row(nw, a, corner_carry<DIFFUSE, T>(s), cx.neg_r, hl, hr);
                     if (s + 1 < T)
                         W[sn][sa] = e;
                     else if (cx.own_x && cx.y0 == 0)
                         st_global_f4(cx.next, e);
                 }
-            } else if (!FAST && s == s_bot && q >= cx.rs + 1) {  // global bottom edge row
+            } else if (!FAST && cx.bot_dom && q == cx.re && q >= cx.rs + 1) {  // global bottom edge row
                 // the adjacent interior row of the last level was stored one step ago by this very lane (the bottom chunk
                 // owns it): read it back instead of keeping every output row alive in registers for this one step
                 const float4 inner = (s + 1 < T) ? W[sn][sa] : ld_global_f4(cx.next + (st.off_out - cx.pitch));
@@ -416,16 +424,6 @@ __device__ __forceinline__ void run_block(const Ctx& cx, Run& st, int rb, int ns
                     st_global_f4(cx.next + st.off_out, e);
             }
         }
-        // 4. the centre row of level s in the NEXT step is row r - s (slot m3(k - s)); it is final now,
-        //    so its west/east shuffles are issued here and complete while the next row is fetched
-#if F2D_SHFL_AHEAD
-#pragma unroll
-        for (int s = 0; s < T; ++s) {
-            const float4 b = W[s][m3(k - s)];
-            wl[s] = __shfl_up_sync(0xffffffffu, b.w, 1);
-            er[s] = __shfl_down_sync(0xffffffffu, b.x, 1);
-        }
-#endif
         st.off_in += cx.pitch;
         st.off_out += cx.pitch;
     }
@@ -534,12 +532,13 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     asm volatile("" : "+r"(cx.pitch), "+r"(cx.rs), "+r"(cx.re), "+r"(cx.y0), "+r"(cx.y1), "+r"(cx.cp_bytes));
     cx.top_dom = (cx.rs == 0) && (g.grow0 == 0);
     cx.bot_dom = (cx.re == g.rows - 1) && (g.grow0 + g.rows == g.grows);
-    const int nsteps = (cx.y1 - 1 + T) - cx.rs + 1;
+    constexpr int LAG = max_lag(T, RHS_REGS);
+    const int nsteps = (cx.y1 - 1 + T + LAG) - cx.rs + 1;
     // absolute input rows r during which some level meets a global edge row:
-    //   top:    q == 1 at level s+1  <=>  r = s + 2,      s in [0, T)
-    //   bottom: q == re at level s+1 <=>  r = re + s + 1, s in [0, T)
-    const int top_lo = cx.top_dom ? 2 : 1 << 30, top_hi = cx.top_dom ? T + 1 : -1;
-    const int bot_lo = cx.bot_dom ? cx.re + 1 : 1 << 30, bot_hi = cx.bot_dom ? cx.re + T : -1;
+    //   top:    q == 1 at level s+1  <=>  r = s + 2 + lag(s),      s in [0, T)
+    //   bottom: q == re at level s+1 <=>  r = re + s + 1 + lag(s), s in [0, T)
+    const int top_lo = cx.top_dom ? 2 : 1 << 30, top_hi = cx.top_dom ? T + 1 + LAG : -1;
+    const int bot_lo = cx.bot_dom ? cx.re + 1 : 1 << 30, bot_hi = cx.bot_dom ? cx.re + T + LAG : -1;
 
     float4 W[T][3];
     float4 RH[NRH];
@@ -581,7 +580,7 @@ __global__ void __launch_bounds__(128, MINB) k_jacobi_stream(Geom g, RelaxBatch 
     }
     Run st;
     st.off_in = (cx.rs + kPFD) * cx.pitch;
-    st.off_out = (cx.rs - T) * cx.pitch;
+    st.off_out = (cx.rs - T - LAG) * cx.pitch;
 
     if (!cx.edge_warp)
         march<T, DIFFUSE, DIVMODE, PIN_ZERO, RHS_REGS, false, RS, NRH>(cx, st, nsteps, top_lo, top_hi, bot_lo, bot_hi, W, RH, wl, er, UV);

@@ -7,7 +7,7 @@ for v in "$@"; do
   case $v in
     ps0) build ps0 -DF2D_PRESSURE_SCALED=0 ;;   # pressure levels unscaled: 4 FADD + FMUL per cell-sweep
     m0)  build m0 -DF2D_RHS_MIRROR=0 ;;         # plain 16-slot rhs ring instead of the mirrored one
-    sa1) build sa1 -DF2D_SHFL_AHEAD=1 ;;        # shuffles issued one row step ahead
+    ls0) build ls0 -DF2D_LEVEL_SPLIT=0 ;;       # all T levels of a row step as one dependent chain
     *) echo "unknown variant $v"; exit 1 ;;
   esac
 done
