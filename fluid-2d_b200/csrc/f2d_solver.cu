@@ -857,6 +857,15 @@ struct f2d_solver {
         return F2D_OK;
     }
 
+    // Size that decides between the pipelined and the serial solve().  The two issue DIFFERENT halo-exchange schedules
+    // (fields one by one vs batched), so every rank of a slab run must take the same path: the decision uses the
+    // nominal interior slab (rows / ranks + two halos), not this rank's own size -- edge slabs are one halo smaller.
+    size_t pipeline_decision_bytes() const {
+        if (!multi()) return field_bytes;
+        const size_t nominal_rows = ((size_t)g.grows + (size_t)nranks - 1) / (size_t)nranks + 2 * (size_t)H();
+        return nominal_rows * (size_t)g.pitch * sizeof(float);
+    }
+
     // rows of the local slab whose cells this solver owns (halo rows excluded)
     int own_begin() const { return (g.grow0 == 0) ? 0 : (int)cfg.halo; }
     int own_end() const { return (g.grow0 + g.rows == g.grows) ? g.rows : g.rows - (int)cfg.halo; }
@@ -1601,7 +1610,7 @@ F2D_API int f2d_solve_host(f2d_solver* s, float* density, const float* density_s
     const size_t host_bytes = (size_t)s->g.rows * s->g.cols * sizeof(float);
     const void* hosts[6] = {density, u, v, density_source, u_source, v_source};
     for (const void* h : hosts) s->pin_host(h, host_bytes);
-    if (s->host_pipeline && !s->cpu_sem() && s->field_bytes >= s->host_pipeline_min_bytes) {
+    if (s->host_pipeline && !s->cpu_sem() && s->pipeline_decision_bytes() >= s->host_pipeline_min_bytes) {
         F2D_TRY(s->solve_host_pipelined(density, density_source, diffusion_rate, u, v, u_source, v_source, viscosity, dt));
         return f2d_sync(s);
     }

@@ -90,22 +90,38 @@ def main():
         if rank == 0:
             ok &= judge("step", glob, single_gpu(n, kd, kp, T, steps, fields, False), steps,
                         dict(n=n, kd=kd, kp=kp, halo=halo, steps=steps, T=T, graph=graph, exchanges=xch))
+            print(json.dumps(report[-1]), flush=True)
         dist.barrier()
 
     # ---- 2. solve() per slab (uploads, the four parts of the step with their exchanges, downloads overlapped) == one GPU.
     #         1024^2 slabs are >= 1 MiB and take the pipelined path; the host slabs carry stale halo rows between calls.
-    for n, kd, kp, halo, steps, T, graph in [(1024, 15, 20, 32, 2, 8, True), (1280, 24, 16, 32, 2, 8, False)]:
+    #         912^2 on 4 ranks and 1280^2 on 8 put the edge slabs below and the interior slabs above the 1 MiB threshold
+    #         of the pipelined path: every rank must still take the same path (same exchange schedule).
+    for n, kd, kp, halo, steps, T, graph in [(1024, 15, 20, 32, 2, 8, True), (1280, 24, 16, 32, 2, 8, False), (912, 15, 20, 32, 2, 8, True)]:
         fields = rng_fields(n, 6000 + n, vel_cells=4.0)
         sl = slabmod.partition(n, world, halo, rank)
         s = make(sl, n, kd, kp, T, graph, 0)
         h = [slabmod.take(sl, a) for a in fields]
-        for _ in range(steps):
-            s.solve(h[0], h[3], DIFFUSION_RATE, h[1], h[2], h[4], h[5], VISCOSITY, DT)
+        failed, msg = False, ""
+        for it in range(steps):
+            try:
+                s.solve(h[0], h[3], DIFFUSION_RATE, h[1], h[2], h[4], h[5], VISCOSITY, DT)
+            except f2d.F2DError as e:
+                failed, msg = True, "rank %d, call %d: %s" % (rank, it, e)
+                print("SOLVE FAILED", msg, flush=True)
+                break
         s.close()
+        if any_rank_failed(failed):
+            if rank == 0:
+                report.append(dict(case="solve", transport=transport, world=world, n=n, graph=graph, ok=False, error=msg or "on another rank"))
+                ok = False
+            dist.barrier()
+            continue
         glob = gather_owned(sl, n, halo, h[:3])
         if rank == 0:
             ok &= judge("solve", glob, single_gpu(n, kd, kp, T, steps, fields, True), steps,
                         dict(n=n, kd=kd, kp=kp, halo=halo, steps=steps, T=T, graph=graph))
+            print(json.dumps(report[-1]), flush=True)
         dist.barrier()
 
     # ---- 3. the displacement bound (CFL) is verified on the device: never a silently wrong state.
