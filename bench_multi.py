@@ -16,6 +16,31 @@ def canonical_rows(n, r0, r1):
     return list(_c.rows(n, r0, r1))
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, before any host buffer exists: the pinned slabs
+    are then first-touched on that node, and solve()'s 36 B per cell of PCIe traffic does not cross the socket link.
+    Host-side placement only (the reference has no notion of it); silently skipped where sysfs or the affinity call
+    are not available."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return {"bound": False, "numa_node": node}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "numa_node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": str(e)[:120]}
+
+
 def single_gpu_base(f2d, n, kd, kp, device=0, steps=5):
     """The N > 1 workload (n x n, Kd, Kp) on ONE GPU, device-resident: the denominator of strong-scaling efficiency.
     Measured inside the run that reports the efficiency (rank 0, after the slab solvers are gone)."""
@@ -46,6 +71,7 @@ def run_multi_gpu(args, workload):
     if world != args.gpus:
         raise SystemExit("launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if os.environ.get("F2D_BENCH_NUMA_BIND", "1") == "1" else {"bound": False}
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, kd, kp = workload["n"], workload["kd"], workload["kp"]
     halo = int(os.environ.get("F2D_HALO", "32"))
@@ -161,7 +187,8 @@ def run_multi_gpu(args, workload):
             "cpu_baseline": cpu if "unavailable" in cpu else {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cells * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(6 * 4 * cells),
                     "d2h_bytes_per_step": int(3 * 4 * cells), "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-                    "api": "FluidSolverB200.solve per slab (pinned host slabs, halo rows included)"},
+                    "api": "FluidSolverB200.solve per slab (pinned host slabs, halo rows included)",
+                    "host_numa_binding_rank0": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "scaling_base": base,
