@@ -39,13 +39,19 @@
 //     and writes it out as the right-hand side of the later passes.
 //   * A host planner (launch_one) sizes the chunks from a cost model so that one launch is exactly
 //     one wave of resident warps that finish together.
-//   * The kernel is bound by instruction issue (profiles/ncu_jacobi_*_T8_r01_final.md), so everything that is not one
-//     of the 5 / 8 floating-point operations per cell is kept out of the row loop: the edge-column fix exists only in
-//     the variant run by the two strips that hold a domain edge column (template parameter EDGE, warp-uniform choice
-//     outside the loop); global rows are addressed with running 32-bit element offsets (one add per step); with the
-//     right-hand side in shared memory (T = 8) its ring is MIRRORED -- 16 slots plus a copy of slots 0..7 behind them
-//     -- so that the T rows r-1 .. r-T a step reads are always contiguous below one pointer and every level reads
-//     its row at a compile-time offset from it (no per-level address arithmetic).
+//   * The kernel is bound by instruction issue (profiles/ncu_jacobi_*_T8_r02_v5.md), so everything that is not one
+//     of the 4 (pressure: levels carried as 4^s * p, see relax_row) / 6 (diffuse: division by the constant 1 + 4a as
+//     a correctly rounded two-operation multiplication, f2d_common.cuh) floating-point operations per cell is kept out
+//     of the row loop: the edge-column fix exists only in the variant run by the two strips that hold a domain edge
+//     column (template parameter EDGE, warp-uniform choice outside the loop); global rows are addressed with running
+//     32-bit element offsets (one add per step); no register copy of the output row is kept (the one edge rule that
+//     needs the previous output row reads it back); with the right-hand side in shared memory (T = 8) its ring is a
+//     plain 16-slot ring, 8 KB-aligned (F2D_RHS_MIRROR=1: the mirrored ring of the first round-2 version, rows written
+//     twice so that every level reads at a compile-time offset -- slower since the instruction diet).
+//   * At T = 8 the levels 4..7 run one row behind the levels 0..3 (level_lag): two independent dependency chains per
+//     row step instead of one.
+//   * The passes are launched with programmatic dependent launch (StreamTuning::pdl): a pass is scheduled and set up
+//     while its predecessor drains and waits with griddepcontrol.wait before it touches global memory.
 //   * A packed fp32x2 variant (FADD2 / FMUL2 / FFMA2, register pairs (x,z) / (y,w)) was built in round 2 and is
 //     bit-identical too, but slower: 72.4 vs 59.1 us per pressure pass, 89 vs 81 us per diffuse pass under ncu at
 //     4096^2 -- the packed operations occupy the FMA pipe for two cycles each (no pipe time saved,
